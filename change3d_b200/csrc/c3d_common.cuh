@@ -1,0 +1,69 @@
+// change3d_b200 — shared device helpers (sm_100a).
+// Activations are fp32 NDHWC: [N, T, H, W, Cs] with channel stride Cs (multiple of 4; the
+// bottleneck's inner width is padded 54->56, 108->112 and the pad lanes are kept at zero).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define C3D_OK 0
+#define C3D_ERR_ARG 1
+#define C3D_ERR_CUDA 2
+#define C3D_ERR_SMEM 3
+
+// BN parameter block written by c3d_bn_finalize: float[4][Cs] = mean, rstd, scale(=gamma*rstd), beta
+#define BNP_MEAN(p, Cs) (p)
+#define BNP_RSTD(p, Cs) ((p) + (Cs))
+#define BNP_SCALE(p, Cs) ((p) + 2 * (Cs))
+#define BNP_BETA(p, Cs) ((p) + 3 * (Cs))
+
+// prologue modes for an operand tile (TileSrc.mode)
+enum { PRO_NONE = 0, PRO_BN_RELU = 1, PRO_BN_GATE_SWISH = 2, PRO_BNBWD = 3, PRO_ABSDIFF = 4, PRO_MASK_POS = 5 };
+// row mappings (TileSrc.map)
+enum { MAP_DENSE = 0, MAP_SUB2 = 1, MAP_CONVT_FWD = 2, MAP_CONVT_BWD = 3 };
+// GEMM epilogues
+enum { EPI_STORE = 0, EPI_RELU_ADD = 1, EPI_SWISH_BWD = 2, EPI_ADD2 = 3, EPI_CONVT = 4, EPI_ABSDIFF_BWD = 5 };
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4relu(float4 a) {
+  return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+}
+// (x - mean) * scale + beta
+__device__ __forceinline__ float4 f4bn(float4 x, float4 mean, float4 scale, float4 beta) {
+  return make_float4(fmaf(x.x - mean.x, scale.x, beta.x), fmaf(x.y - mean.y, scale.y, beta.y),
+                     fmaf(x.z - mean.z, scale.z, beta.z), fmaf(x.w - mean.w, scale.w, beta.w));
+}
+__device__ __forceinline__ float swishf_(float u) { return u * sigmoidf_(u); }
+__device__ __forceinline__ float swish_gradf_(float u) {
+  float s = sigmoidf_(u);
+  return s * (1.0f + u * (1.0f - s));
+}
+
+static inline int c3d_check_last(cudaError_t e) { return e == cudaSuccess ? C3D_OK : C3D_ERR_CUDA; }
+
+// Operand descriptor for the pointwise-GEMM family (see pw_gemm.cu).
+struct TileSrc {
+  const float* A;      // primary tensor
+  const float* A2;     // secondary (y for PRO_BNBWD, second frame for PRO_ABSDIFF)
+  const float* bnp;    // [4][ld]
+  const float* coef;   // [2][ld]: c1 = mean(d), c2 = mean(d * yhat)      (PRO_BNBWD)
+  const float* gate;   // [samples][ld]                                   (PRO_BN_GATE_SWISH, may be null)
+  int mode, map;
+  int ld;              // row stride (channels incl. pad) of A / A2
+  int K;               // staged width: ld, or 4*ld / 16*ld for the ConvTranspose gathers
+  int OHW, OW;         // GEMM row -> (img, oh, ow)
+  int IH, IW;          // source spatial dims
+  long long img_stride, img_stride2;  // elements between consecutive images of A / A2
+  int frames_per_sample;
+  int cls;             // ConvTranspose parity class (py*2+px) for MAP_CONVT_FWD
+  int seg0;            // first gathered tap staged (gather maps)
+};

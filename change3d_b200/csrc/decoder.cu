@@ -1,0 +1,182 @@
+// ChangeDecoder head (model/change_decoder.py:53-55,76-79): Conv2d 3x3 (C -> ncls, pad 1, no bias)
+// [+ sigmoid], NHWC in, NCHW out (the layout the reference returns), and its backward.
+// The 1x1 Conv2d + ConvTranspose2d up-blocks run through the pointwise-GEMM family (pw_gemm.cu).
+#include "c3d_common.cuh"
+#include "../../include/change3d_b200.h"
+
+#define HEAD_MAX_CLS 8
+
+__global__ void __launch_bounds__(256) dec_head_fwd_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                           float* __restrict__ Y, int H, int W, int C, int ncls,
+                                                           int apply_sigmoid) {
+  extern __shared__ __align__(16) float ws[];   // [9][ncls][C]
+  for (int i = threadIdx.x; i < 9 * ncls * C; i += 256) {
+    int c = i % C, k = (i / C) % ncls, tap = i / (C * ncls);
+    ws[i] = __ldg(w + (k * C + c) * 9 + tap);
+  }
+  __syncthreads();
+  const int n = blockIdx.z;
+  const int ow = blockIdx.x * 32 + (threadIdx.x & 31), oh = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ow >= W || oh >= H) return;
+  float acc[HEAD_MAX_CLS];
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_CLS; ++k) acc[k] = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = oh - 1 + kh;
+    if (ih < 0 || ih >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = ow - 1 + kw;
+      if (iw < 0 || iw >= W) continue;
+      const float* xp = X + (((long long)n * H + ih) * W + iw) * C;
+      const float* wp = ws + (kh * 3 + kw) * ncls * C;
+      for (int c = 0; c < C; c += 4) {
+        const float4 x = ldg4(xp + c);
+#pragma unroll
+        for (int k = 0; k < HEAD_MAX_CLS; ++k) {
+          if (k < ncls) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + k * C + c);
+            acc[k] = fmaf(x.x, wv.x, fmaf(x.y, wv.y, fmaf(x.z, wv.z, fmaf(x.w, wv.w, acc[k]))));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HEAD_MAX_CLS; ++k) {
+    if (k < ncls) {
+      float v = acc[k];
+      if (apply_sigmoid) v = 1.0f / (1.0f + expf(-v));
+      Y[(((long long)n * ncls + k) * H + oh) * W + ow] = v;
+    }
+  }
+}
+
+extern "C" int c3d_dec_head_fwd(const float* X, const float* w, float* Y, int B, int H, int W, int C, int ncls,
+                                int apply_sigmoid, void* stream_) {
+  if (!X || !w || !Y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || ncls <= 0 || ncls > HEAD_MAX_CLS)
+    return C3D_ERR_ARG;
+  dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+  size_t smem = (size_t)9 * ncls * C * sizeof(float);
+  dec_head_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(X, w, Y, H, W, C, ncls, apply_sigmoid);
+  return c3d_check_last(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head backward: dlogit = dpred * p * (1 - p) (sigmoid head) or dpred;
+//   dX[i][ci]      = sum_{k,tap} w[k][ci][tap] * dlogit[i - off(tap)][k]
+//   dW[k][ci][tap] += sum_o dlogit[o][k] * X[o + off(tap)][ci]
+// Persistent CTAs over 32x8 tiles; dlogit and X tiles (with a 1-pixel halo) staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+#define HEAD_XLD 28
+
+__global__ void __launch_bounds__(256) dec_head_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ pred,
+                                                           const float* __restrict__ X, const float* __restrict__ w,
+                                                           float* __restrict__ dX, float* __restrict__ dW, int B, int H,
+                                                           int W, int C, int ncls, int is_sigmoid) {
+  constexpr int PW = 34, PH = 10, NPIX = PW * PH;
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                        // [9][ncls][C]
+  float* dl = ws + 9 * ncls * C;         // [ncls][NPIX]
+  float* xs = dl + ncls * NPIX;          // [NPIX][HEAD_XLD]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * ncls * C; i += 256) {
+    int c = i % C, k = (i / C) % ncls, tap = i / (C * ncls);
+    ws[i] = __ldg(w + (k * C + c) * 9 + tap);
+  }
+  const int nq = C >> 2;
+  const int nitems = ncls * nq * 9;      // wgrad owners: (k, quad, tap)
+  float4 wacc[2] = {f4zero(), f4zero()};
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8, ntiles = tiles_x * tiles_y * B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int trem = tile - n * tiles_x * tiles_y;
+    const int h0 = (trem / tiles_x) * 8, w0 = (trem % tiles_x) * 32;
+    __syncthreads();
+    for (int i = tid; i < ncls * NPIX; i += 256) {
+      int k = i / NPIX, p = i - k * NPIX, y = p / PW, x = p - y * PW;
+      int h = h0 - 1 + y, ww = w0 - 1 + x;
+      float v = 0.f;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) {
+        const long long off = (((long long)n * ncls + k) * H + h) * W + ww;
+        v = __ldg(dpred + off);
+        if (is_sigmoid) { const float p_ = __ldg(pred + off); v *= p_ * (1.f - p_); }
+      }
+      dl[i] = v;
+    }
+    for (int i = tid; i < NPIX * nq; i += 256) {
+      int p = i / nq, q = i - p * nq, y = p / PW, x = p - y * PW;
+      int h = h0 - 1 + y, ww = w0 - 1 + x;
+      float4 v = f4zero();
+      if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
+      *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v;
+    }
+    __syncthreads();
+    // dgrad: one thread per interior pixel
+    {
+      const int lx = tid & 31, ly = tid >> 5;
+      const int h = h0 + ly, ww = w0 + lx;
+      if (h < H && ww < W) {
+        for (int q = 0; q < nq; ++q) {
+          float4 acc = f4zero();
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+              // out pixel o = i - off(tap) with off = (kh-1, kw-1): tile coords (ly+1-(kh-1), lx+1-(kw-1))
+              const int p = (ly + 2 - kh) * PW + (lx + 2 - kw);
+              for (int k = 0; k < ncls; ++k) {
+                const float d = dl[k * NPIX + p];
+                const float4 wv = *reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * ncls + k) * C + 4 * q);
+                acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y); acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
+              }
+            }
+          st4(dX + (((long long)n * H + h) * W + ww) * C + 4 * q, acc);
+        }
+      }
+    }
+    // wgrad owners
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int item = tid + it * 256;
+      if (item >= nitems) break;
+      const int tap = item % 9, q = (item / 9) % nq, k = item / (9 * nq);
+      const int kh = tap / 3, kw = tap - kh * 3;
+      float4 a = wacc[it];
+      for (int y = 1; y <= 8; ++y) {
+        const float* dp = dl + k * NPIX + y * PW;
+        const float* xp = xs + ((y - 1 + kh) * PW + kw) * HEAD_XLD + 4 * q;
+#pragma unroll 4
+        for (int x = 1; x <= 32; ++x) {
+          const float d = dp[x];
+          const float4 xv = *reinterpret_cast<const float4*>(xp + (x - 1) * HEAD_XLD);
+          a.x = fmaf(d, xv.x, a.x); a.y = fmaf(d, xv.y, a.y); a.z = fmaf(d, xv.z, a.z); a.w = fmaf(d, xv.w, a.w);
+        }
+      }
+      wacc[it] = a;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int item = tid + it * 256;
+    if (item >= nitems) break;
+    const int tap = item % 9, q = (item / 9) % nq, k = item / (9 * nq);
+    atomicAdd(dW + (k * C + 4 * q + 0) * 9 + tap, wacc[it].x); atomicAdd(dW + (k * C + 4 * q + 1) * 9 + tap, wacc[it].y);
+    atomicAdd(dW + (k * C + 4 * q + 2) * 9 + tap, wacc[it].z); atomicAdd(dW + (k * C + 4 * q + 3) * 9 + tap, wacc[it].w);
+  }
+}
+
+extern "C" int c3d_dec_head_bwd(const float* dpred, const float* pred, const float* X, const float* w, float* dX,
+                                float* dW, int B, int H, int W, int C, int ncls, int is_sigmoid, void* stream_) {
+  if (!dpred || !X || !w || !dX || !dW || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || C > 24 || ncls <= 0 ||
+      ncls > HEAD_MAX_CLS)
+    return C3D_ERR_ARG;
+  if (is_sigmoid && !pred) return C3D_ERR_ARG;
+  if (ncls * (C >> 2) * 9 > 512) return C3D_ERR_ARG;
+  const size_t smem = (size_t)(9 * ncls * C + ncls * 340 + 340 * HEAD_XLD) * sizeof(float);
+  cudaFuncSetAttribute(dec_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = ((W + 31) / 32) * ((H + 7) / 8) * B;
+  int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
+  dec_head_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(dpred, pred, X, w, dX, dW, B, H, W, C, ncls, is_sigmoid);
+  return c3d_check_last(cudaGetLastError());
+}

@@ -1,0 +1,366 @@
+// BatchNorm3d finalisation (statistics -> parameter block, running-stat update), the SqueezeExcitation
+// gate, the fused residual join, and their backward counterparts.
+// Reference: nn.BatchNorm3d sites model/x3d.py:94-98,176-180,203-208,217-221,296-298; fvcore
+// SqueezeExcitation call site model/x3d.py:194-202; ResBlock fusion model/x3d.py:326-327.
+#include "c3d_common.cuh"
+#include "../../include/change3d_b200.h"
+
+__device__ __forceinline__ void bn_params_for_channel(const double* stats, int groups, long long count,
+                                                      const float* gamma, const float* beta, float* rm, float* rv,
+                                                      int c, int Cs, float momentum, float eps, int training,
+                                                      bool write_running, float& mean_f, float& rstd_f) {
+  double mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int g = 0; g < groups; ++g) {
+      s += stats[((long long)g * 2 + 0) * Cs + c];
+      q += stats[((long long)g * 2 + 1) * Cs + c];
+    }
+    mean = s / (double)count;
+    var = q / (double)count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (write_running && rm && rv) {
+      double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+      rm[c] = (float)((1.0 - (double)momentum) * (double)rm[c] + (double)momentum * mean);
+      rv[c] = (float)((1.0 - (double)momentum) * (double)rv[c] + (double)momentum * unbiased);
+    }
+  } else {
+    mean = (double)rm[c];
+    var = (double)rv[c];
+  }
+  mean_f = (float)mean;
+  rstd_f = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void bn_finalize_kernel(const double* stats, int groups, long long count, const float* gamma,
+                                   const float* beta, float* rm, float* rv, int C, int Cs, float momentum, float eps,
+                                   int training, float* bnp) {
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    if (c >= C) {
+      bnp[c] = 0.f; bnp[Cs + c] = 0.f; bnp[2 * Cs + c] = 0.f; bnp[3 * Cs + c] = 0.f;
+      continue;
+    }
+    float mean, rstd;
+    bn_params_for_channel(stats, groups, count, gamma, beta, rm, rv, c, Cs, momentum, eps, training, true, mean, rstd);
+    bnp[c] = mean; bnp[Cs + c] = rstd; bnp[2 * Cs + c] = gamma[c] * rstd; bnp[3 * Cs + c] = beta[c];
+  }
+}
+
+extern "C" int c3d_bn_finalize(const double* stats, int groups, long long count, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, int C, int Cs, float momentum, float eps,
+                               int training, float* bnp, void* stream_) {
+  if (!gamma || !beta || !bnp || C <= 0 || Cs < C) return C3D_ERR_ARG;
+  if (training ? (!stats || groups <= 0 || count <= 0) : (!running_mean || !running_var)) return C3D_ERR_ARG;
+  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(stats, groups, count, gamma, beta, running_mean,
+                                                            running_var, C, Cs, momentum, eps, training, bnp);
+  return c3d_check_last(cudaGetLastError());
+}
+
+// one CTA per batch sample; every CTA derives the BN parameters (cheap), CTA 0 publishes them
+__global__ void __launch_bounds__(256) bn_se_finalize_kernel(
+    const double* stats, int N, long long cnt, const float* gamma, const float* beta, float* rm, float* rv, int C,
+    int Cs, float momentum, float eps, int training, const float* w1, const float* b1, const float* w2,
+    const float* b2, int R, float* bnp, float* zhat_mean, float* hidden, float* gate) {
+  extern __shared__ float sm[];
+  float* pooled = sm;          // [Cs]
+  float* hid = sm + Cs;        // [R]
+  const int n = blockIdx.x;
+  const long long count = cnt * N;
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float zm = 0.f, pl = 0.f;
+    if (c < C) {
+      float mean, rstd;
+      bn_params_for_channel(stats, N, count, gamma, beta, rm, rv, c, Cs, momentum, eps, training, n == 0, mean, rstd);
+      const float scale = gamma[c] * rstd, bt = beta[c];
+      if (n == 0) { bnp[c] = mean; bnp[Cs + c] = rstd; bnp[2 * Cs + c] = scale; bnp[3 * Cs + c] = bt; }
+      const float m_n = (float)(stats[((long long)n * 2) * Cs + c] / (double)cnt);
+      zm = (m_n - mean) * rstd;
+      pl = fmaf(m_n - mean, scale, bt);
+    } else if (n == 0) {
+      bnp[c] = 0.f; bnp[Cs + c] = 0.f; bnp[2 * Cs + c] = 0.f; bnp[3 * Cs + c] = 0.f;
+    }
+    pooled[c] = pl;
+    if (zhat_mean) zhat_mean[(long long)n * Cs + c] = zm;
+  }
+  if (!w1) return;   // BN only
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += 8) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[r * C + c], pooled[c], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      s = fmaxf(s + b1[r], 0.f);
+      hid[r] = s;
+      hidden[(long long)n * R + r] = s;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float g = 0.f;
+    if (c < C) {
+      float s = b2[c];
+      for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
+      g = sigmoidf_(s);
+    }
+    gate[(long long)n * Cs + c] = g;
+  }
+}
+
+extern "C" int c3d_bn_se_finalize(const double* stats, int N, long long count_per_sample, const float* gamma,
+                                  const float* beta, float* running_mean, float* running_var, int C, int Cs,
+                                  float momentum, float eps, int training, const float* w1, const float* b1,
+                                  const float* w2, const float* b2, int R, float* bnp, float* zhat_mean, float* hidden,
+                                  float* gate, void* stream_) {
+  if (!stats || !gamma || !beta || !bnp || N <= 0 || count_per_sample <= 0 || C <= 0 || Cs < C) return C3D_ERR_ARG;
+  if (!training && (!running_mean || !running_var)) return C3D_ERR_ARG;
+  if (w1 && (!b1 || !w2 || !b2 || R <= 0 || !hidden || !gate)) return C3D_ERR_ARG;
+  size_t smem = (size_t)(Cs + (R > 0 ? R : 0)) * sizeof(float);
+  bn_se_finalize_kernel<<<N, 256, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, gamma, beta, running_mean,
+                                                                 running_var, C, Cs, momentum, eps, training, w1, b1,
+                                                                 w2, b2, R, bnp, zhat_mean, hidden, gate);
+  return c3d_check_last(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restrict__ A, const float* __restrict__ bnpA,
+                                                          const float* __restrict__ B, const float* __restrict__ bnpB,
+                                                          float* __restrict__ Y, long long total4, int Cs) {
+  const int q4 = Cs >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % q4) * 4;
+    float4 v = f4bn(ldg4(A + i * 4), ldg4(bnpA + c), ldg4(bnpA + 2 * Cs + c), ldg4(bnpA + 3 * Cs + c));
+    if (B) {
+      float4 b = ldg4(B + i * 4);
+      if (bnpB) b = f4bn(b, ldg4(bnpB + c), ldg4(bnpB + 2 * Cs + c), ldg4(bnpB + 3 * Cs + c));
+      v = f4add(v, b);
+    }
+    st4(Y + i * 4, f4relu(v));
+  }
+}
+
+extern "C" int c3d_bn_add_relu(const float* A, const float* bnpA, const float* B, const float* bnpB, float* Y,
+                               long long M, int Cs, void* stream_) {
+  if (!A || !bnpA || !Y || M <= 0 || Cs <= 0 || (Cs & 3)) return C3D_ERR_ARG;
+  const long long total4 = M * (Cs >> 2);
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_add_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(A, bnpA, B, bnpB, Y, total4, Cs);
+  return c3d_check_last(cudaGetLastError());
+}
+
+extern "C" int c3d_version(void) { return C3D_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+
+// d_pre = dOut * (out > 0)   [ResBlock / stem ReLU backward]
+// stats_c += (sum d_pre, sum d_pre * yhat_c)  and, for a normalised shortcut, stats_1 likewise.
+// Threads keep a fixed channel quad so the column sums stay in registers.
+__global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
+    const float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ yc,
+    const float* __restrict__ bnp_c, const float* __restrict__ y1, const float* __restrict__ bnp_1,
+    float* __restrict__ d_pre, double* __restrict__ stats_c, double* __restrict__ stats_1, long long M, int Cs) {
+  extern __shared__ float sm[];   // [3][Cs]
+  for (int i = threadIdx.x; i < 3 * Cs; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const int q4 = Cs >> 2;
+  const int rpb = 256 / q4;
+  const int tid = threadIdx.x;
+  if (tid < rpb * q4) {
+    const int q = tid % q4, rl = tid / q4, c = 4 * q;
+    const float4 mc = ldg4(bnp_c + c), rc = ldg4(bnp_c + Cs + c);
+    float4 m1 = f4zero(), r1 = f4zero();
+    if (y1) { m1 = ldg4(bnp_1 + c); r1 = ldg4(bnp_1 + Cs + c); }
+    float4 s = f4zero(), tc = f4zero(), t1 = f4zero();
+    for (long long row = (long long)blockIdx.x * rpb + rl; row < M; row += (long long)gridDim.x * rpb) {
+      const long long off = row * Cs + c;
+      float4 d = ldg4(dOut + off);
+      const float4 o = ldg4(out + off);
+      d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+      st4(d_pre + off, d);
+      const float4 y = ldg4(yc + off);
+      s = f4add(s, d);
+      tc.x = fmaf(d.x, (y.x - mc.x) * rc.x, tc.x); tc.y = fmaf(d.y, (y.y - mc.y) * rc.y, tc.y);
+      tc.z = fmaf(d.z, (y.z - mc.z) * rc.z, tc.z); tc.w = fmaf(d.w, (y.w - mc.w) * rc.w, tc.w);
+      if (y1) {
+        const float4 z = ldg4(y1 + off);
+        t1.x = fmaf(d.x, (z.x - m1.x) * r1.x, t1.x); t1.y = fmaf(d.y, (z.y - m1.y) * r1.y, t1.y);
+        t1.z = fmaf(d.z, (z.z - m1.z) * r1.z, t1.z); t1.w = fmaf(d.w, (z.w - m1.w) * r1.w, t1.w);
+      }
+    }
+    atomicAdd(&sm[c], s.x); atomicAdd(&sm[c + 1], s.y); atomicAdd(&sm[c + 2], s.z); atomicAdd(&sm[c + 3], s.w);
+    atomicAdd(&sm[Cs + c], tc.x); atomicAdd(&sm[Cs + c + 1], tc.y); atomicAdd(&sm[Cs + c + 2], tc.z); atomicAdd(&sm[Cs + c + 3], tc.w);
+    if (y1) {
+      atomicAdd(&sm[2 * Cs + c], t1.x); atomicAdd(&sm[2 * Cs + c + 1], t1.y);
+      atomicAdd(&sm[2 * Cs + c + 2], t1.z); atomicAdd(&sm[2 * Cs + c + 3], t1.w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cs; i += 256) {
+    atomicAdd(stats_c + i, (double)sm[i]);
+    atomicAdd(stats_c + Cs + i, (double)sm[Cs + i]);
+    if (y1) {
+      atomicAdd(stats_1 + i, (double)sm[i]);
+      atomicAdd(stats_1 + Cs + i, (double)sm[2 * Cs + i]);
+    }
+  }
+}
+
+extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const float* y_c, const float* bnp_c,
+                                  const float* y_1, const float* bnp_1, float* d_pre, double* stats_c, double* stats_1,
+                                  long long M, int Cs, void* stream_) {
+  if (!dOut || !out || !y_c || !bnp_c || !d_pre || !stats_c || M <= 0 || Cs <= 0 || (Cs & 3) || Cs > 1024) return C3D_ERR_ARG;
+  if (y_1 && (!bnp_1 || !stats_1)) return C3D_ERR_ARG;
+  const int rpb = 256 / (Cs >> 2);
+  long long blocks = (M + rpb - 1) / rpb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  relu_bwd_stats_kernel<<<(unsigned)blocks, 256, 3 * Cs * sizeof(float), (cudaStream_t)stream_>>>(
+      dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
+  return c3d_check_last(cudaGetLastError());
+}
+
+// stats = double[groups][2][Cs] (sum d, sum d*yhat) -> coef[2][Cs] = (mean d, mean d*yhat); dgamma, dbeta
+__global__ void bn_bwd_finalize_kernel(const double* stats, int groups, long long count, int C, int Cs, float* coef,
+                                       float* dgamma, float* dbeta) {
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    double s = 0.0, t = 0.0;
+    if (c < C)
+      for (int g = 0; g < groups; ++g) { s += stats[((long long)g * 2) * Cs + c]; t += stats[((long long)g * 2 + 1) * Cs + c]; }
+    coef[c] = (float)(s / (double)count);
+    coef[Cs + c] = (float)(t / (double)count);
+    if (c < C) { dgamma[c] = (float)t; dbeta[c] = (float)s; }
+  }
+}
+
+extern "C" int c3d_bn_bwd_finalize(const double* stats, int groups, long long count, int C, int Cs, float* coef,
+                                   float* dgamma, float* dbeta, void* stream_) {
+  if (!stats || !coef || !dgamma || !dbeta || groups <= 0 || count <= 0 || C <= 0 || Cs < C) return C3D_ERR_ARG;
+  bn_bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(stats, groups, count, C, Cs, coef, dgamma, dbeta);
+  return c3d_check_last(cudaGetLastError());
+}
+
+// SE backward + BN_b backward coefficients.  stats = double[N][2][Cs]: per-sample (sum du, sum du*zhat).
+__global__ void __launch_bounds__(256) se_bn_bwd_finalize_kernel(
+    const double* __restrict__ stats, int N, long long cnt, const float* __restrict__ bnp, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ gate, const float* __restrict__ hidden,
+    const float* __restrict__ zhat_mean, const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cs, int R,
+    float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dpool,
+    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
+  extern __shared__ float sm[];
+  float* dps = sm;               // [N][C]   grad wrt pre-sigmoid
+  float* dpr = sm + (size_t)N * C;   // [N][R]   grad wrt pre-relu
+  const int tid = threadIdx.x;
+  const bool se = (gate != nullptr);
+  const double Mtot = (double)cnt * (double)N;
+  if (se) {
+    for (int i = tid; i < N * C; i += 256) {
+      const int n = i / C, c = i - n * C;
+      const double A = stats[((long long)n * 2) * Cs + c], Bz = stats[((long long)n * 2 + 1) * Cs + c];
+      const float g = gate[(long long)n * Cs + c];
+      const float dg = (float)((double)gamma[c] * Bz + (double)beta[c] * A);   // sum du * z
+      dps[i] = dg * g * (1.f - g);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s += dps[n * C + c];
+      db2[c] = s;
+    }
+    for (int i = tid; i < C * R; i += 256) {
+      const int c = i / R, r = i - c * R;
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s = fmaf(dps[n * C + c], hidden[(long long)n * R + r], s);
+      dw2[i] = s;
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < N * R; i += 8) {
+      const int n = i / R, r = i - n * R;
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s = fmaf(w2[c * R + r], dps[n * C + c], s);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) dpr[i] = hidden[(long long)n * R + r] > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += 256) {
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s += dpr[n * R + r];
+      db1[r] = s;
+    }
+    for (int i = tid; i < R * C; i += 256) {
+      const int r = i / C, c = i - r * C;
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s = fmaf(dpr[n * R + r], fmaf(zhat_mean[(long long)n * Cs + c], gamma[c], beta[c]), s);
+      dw1[i] = s;
+    }
+  }
+  for (int c = tid; c < Cs; c += 256) {
+    double S1 = 0.0, S2 = 0.0;
+    if (c < C) {
+      for (int n = 0; n < N; ++n) {
+        const double A = stats[((long long)n * 2) * Cs + c], Bz = stats[((long long)n * 2 + 1) * Cs + c];
+        if (se) {
+          float dp = 0.f;
+          for (int r = 0; r < R; ++r) dp = fmaf(w1[r * C + c], dpr[n * R + r], dp);
+          const double g = (double)gate[(long long)n * Cs + c];
+          S1 += g * A + (double)dp;
+          S2 += g * Bz + (double)dp * (double)zhat_mean[(long long)n * Cs + c];
+          dpool[(long long)n * Cs + c] = (float)((double)dp / (double)cnt);
+        } else {
+          S1 += A; S2 += Bz;
+        }
+      }
+      dgamma[c] = (float)S2;
+      dbeta[c] = (float)S1;
+    } else if (se) {
+      for (int n = 0; n < N; ++n) dpool[(long long)n * Cs + c] = 0.f;
+    }
+    coef[c] = (float)(S1 / Mtot);
+    coef[Cs + c] = (float)(S2 / Mtot);
+  }
+}
+
+extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long count_per_sample, const float* bnp,
+                                      const float* gamma, const float* beta, const float* gate, const float* hidden,
+                                      const float* zhat_mean, const float* w1, const float* w2, int C, int Cs, int R,
+                                      float* coef, float* dgamma, float* dbeta, float* dpool, float* dw1, float* db1,
+                                      float* dw2, float* db2, void* stream_) {
+  if (!stats || !bnp || !gamma || !beta || !coef || !dgamma || !dbeta || N <= 0 || count_per_sample <= 0 || C <= 0 || Cs < C)
+    return C3D_ERR_ARG;
+  if (gate && (!hidden || !zhat_mean || !w1 || !w2 || !dpool || !dw1 || !db1 || !dw2 || !db2 || R <= 0)) return C3D_ERR_ARG;
+  size_t smem = gate ? ((size_t)N * C + (size_t)N * R) * sizeof(float) : 0;
+  if (smem > 200 * 1024) return C3D_ERR_SMEM;
+  cudaFuncSetAttribute(se_bn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  se_bn_bwd_finalize_kernel<<<1, 256, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, bnp, gamma, beta, gate,
+                                                                    hidden, zhat_mean, w1, w2, C, Cs, R, coef, dgamma,
+                                                                    dbeta, dpool, dw1, db1, dw2, db2);
+  return c3d_check_last(cudaGetLastError());
+}
+
+// out[c] += sum over rows of X[row][c]  (ConvTranspose2d bias gradient)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, long long M, int Cs, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  for (int i = threadIdx.x; i < Cs; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const int q4 = Cs >> 2, rpb = 256 / q4, tid = threadIdx.x;
+  if (tid < rpb * q4) {
+    const int q = tid % q4, rl = tid / q4;
+    float4 s = f4zero();
+    for (long long row = (long long)blockIdx.x * rpb + rl; row < M; row += (long long)gridDim.x * rpb)
+      s = f4add(s, ldg4(X + row * Cs + 4 * q));
+    atomicAdd(&sm[4 * q], s.x); atomicAdd(&sm[4 * q + 1], s.y); atomicAdd(&sm[4 * q + 2], s.z); atomicAdd(&sm[4 * q + 3], s.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cs; i += 256) atomicAdd(out + i, sm[i]);
+}
+
+extern "C" int c3d_colsum(const float* X, long long M, int Cs, float* out, void* stream_) {
+  if (!X || !out || M <= 0 || Cs <= 0 || (Cs & 3) || Cs > 1024) return C3D_ERR_ARG;
+  const int rpb = 256 / (Cs >> 2);
+  long long blocks = (M + rpb - 1) / rpb;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  colsum_kernel<<<(unsigned)blocks, 256, Cs * sizeof(float), (cudaStream_t)stream_>>>(X, M, Cs, out);
+  return c3d_check_last(cudaGetLastError());
+}

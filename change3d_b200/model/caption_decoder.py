@@ -1,0 +1,116 @@
+"""CaptionDecoder — counterpart of the reference's `model/caption_decoder.py:272-612` (CC task).
+
+Scope note: the captioning head is < 1 % of the FLOPs of a CC step; the
+B200-native part of CC is the encoder feature path (X3D stem..res5 through change3d_b200 kernels,
+`Encoder.forward(..., output_final=True)`).  This head therefore keeps torch's MultiheadAttention /
+LayerNorm / Linear ops, with the reference's module tree so its checkpoints load: every parameter the
+reference registers is registered here under the same name, including the ones its forward never uses
+(self_attn2, multihead_attn, multihead_attn3, linear1/2, norm3, fc_alpha1-3, embedding_1D).
+
+Two deliberate fixes relative to the reference, neither changing the arithmetic:
+  * the decoder layer accepts (and ignores) the `tgt_is_causal` / `memory_is_causal` keywords that
+    nn.TransformerDecoder passes on torch >= 2.0 (the reference layer raises TypeError there);
+  * the causal mask is built on the input's device instead of `.cuda()`.
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .utils import weight_init
+
+
+class PositionalEncoding(nn.Module):
+    """Fixed sinusoidal table added to the token embeddings (model/caption_decoder.py:272-313)."""
+
+    def __init__(self, d_model, dropout=0.1, max_len=5000):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        freq = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        table = torch.zeros(max_len, d_model)
+        table[:, 0::2] = torch.sin(pos * freq)
+        table[:, 1::2] = torch.cos(pos * freq)
+        self.register_buffer('pe', table.unsqueeze(1))
+        self.embedding_1D = nn.Embedding(52, int(d_model))    # registered by the reference, unused
+
+    def forward(self, x):
+        return self.dropout(x + self.pe[:x.size(0), :])
+
+
+class Mesh_TransformerDecoderLayer(nn.Module):
+    """Live path (model/caption_decoder.py:411-423): norm1(tgt + SA(tgt)) -> norm2(. + MHA2(., memory))."""
+    __constants__ = ['batch_first', 'norm_first']
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, layer_norm_eps=1e-5,
+                 batch_first=False, norm_first=False, device=None, dtype=None):
+        super().__init__()
+        mha = lambda: nn.MultiheadAttention(int(d_model), int(nhead), dropout=dropout)   # noqa: E731
+        self.self_attn = mha()
+        self.self_attn2 = mha()
+        self.multihead_attn = mha()
+        self.multihead_attn2 = mha()
+        self.multihead_attn3 = mha()
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm_first = norm_first
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm3 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        for i in range(1, 6):
+            setattr(self, f"dropout{i}", nn.Dropout(dropout))
+        self.activation = nn.ReLU()
+        self.activation2 = nn.Softmax(dim=-1)
+        for i in range(1, 4):
+            lin = nn.Linear(2 * d_model, d_model)
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.constant_(lin.bias, 0)
+            setattr(self, f"fc_alpha{i}", lin)
+        weight_init(self)
+
+    def forward(self, tgt: Tensor, memory: Tensor, tgt_mask: Optional[Tensor] = None,
+                memory_mask: Optional[Tensor] = None, tgt_key_padding_mask: Optional[Tensor] = None,
+                memory_key_padding_mask: Optional[Tensor] = None, **_ignored) -> Tensor:
+        sa = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask,
+                            need_weights=False)[0]
+        x = self.norm1(tgt + self.dropout1(sa))
+        ca, _ = self.multihead_attn2(x, memory, memory, attn_mask=memory_mask,
+                                     key_padding_mask=memory_key_padding_mask, need_weights=True)
+        return self.norm2(x + self.dropout3(ca))
+
+
+class CaptionDecoder(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        print(f"decoder_n_layers={args.n_layer}")
+        self.vocab_embedding = nn.Embedding(args.vocab_size, args.embed_dim)
+        layer = Mesh_TransformerDecoderLayer(args.embed_dim, args.n_head, dim_feedforward=args.embed_dim * 4,
+                                             dropout=args.dropout)
+        self.transformer = nn.TransformerDecoder(layer, args.n_layer)
+        self.position_encoding = PositionalEncoding(args.embed_dim)
+        self.wdc = nn.Linear(args.embed_dim, args.vocab_size)
+        self.dropout_layer = nn.Dropout(p=args.dropout)
+        self.init_weights()
+
+    def init_weights(self):
+        self.vocab_embedding.weight.data.uniform_(-0.1, 0.1)
+        self.wdc.bias.data.fill_(0)
+        self.wdc.weight.data.uniform_(-0.1, 0.1)
+
+    def forward(self, memory, encoded_captions, caption_lengths):
+        """(memory (S,B,D), captions (B,L) int64, lengths (B,1)) -> (pred (B,L,V) sorted by length, sorted
+        captions, decode lengths, sort indices) — model/caption_decoder.py:574-612."""
+        tgt = encoded_captions.permute(1, 0)
+        L = tgt.size(0)
+        mask = torch.full((L, L), float('-inf'), device=tgt.device).triu(diagonal=1)
+        emb = self.position_encoding(self.vocab_embedding(tgt))
+        pred = self.transformer(emb, memory, tgt_mask=mask)
+        pred = self.wdc(self.dropout_layer(pred)).permute(1, 0, 2)
+        caption_lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
+        encoded_captions = encoded_captions[sort_ind]
+        pred = pred[sort_ind]
+        decode_lengths = (caption_lengths - 1).tolist()
+        return pred, encoded_captions, decode_lengths, sort_ind

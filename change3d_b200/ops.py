@@ -1,0 +1,239 @@
+"""Op-level wrappers over the C ABI (include/change3d_b200.h).
+
+torch is used for device memory and streams only; every function below launches hand-written
+sm_100a kernels from libchange3d_b200.so and raises if the library or a CUDA device is missing.
+Activations are fp32 NDHWC torch tensors of shape (N, T, H, W, Cs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_CONVT, EPI_RELU_ADD, EPI_STORE, EPI_SWISH_BWD, MAP_CONVT_BWD,
+                   MAP_CONVT_FWD, MAP_DENSE, MAP_SUB2, PRO_ABSDIFF, PRO_BN_GATE_SWISH, PRO_BN_RELU, PRO_BNBWD,
+                   PRO_MASK_POS, PRO_NONE)
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def pad8(c: int) -> int:
+    """Channel stride of the bottleneck's inner tensors (54->56, 108->112, 216, 432)."""
+    return (c + 7) // 8 * 8
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("change3d_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def operand(A: torch.Tensor, *, ld: int, OH: int, OW: int, IH: Optional[int] = None, IW: Optional[int] = None,
+            img_stride: Optional[int] = None, mode: int = PRO_NONE, map_: int = MAP_DENSE,
+            A2: Optional[torch.Tensor] = None, img_stride2: int = 0, bnp: Optional[torch.Tensor] = None,
+            coef: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+            frames_per_sample: int = 1, seg0: int = 0, nseg: int = 0) -> L.Operand:
+    IH = OH if IH is None else IH
+    IW = OW if IW is None else IW
+    if img_stride is None:
+        img_stride = IH * IW * ld
+    o = L.Operand()
+    o.A = _ptr(A); o.A2 = _ptr(A2); o.bnp = _ptr(bnp); o.coef = _ptr(coef); o.gate = _ptr(gate)
+    o.mode = mode; o.map = map_; o.ld = ld
+    o.OH = OH; o.OW = OW; o.IH = IH; o.IW = IW
+    o.img_stride = img_stride; o.img_stride2 = img_stride2
+    o.frames_per_sample = frames_per_sample
+    o.seg0 = seg0; o.nseg = nseg
+    return o
+
+
+def pw_gemm(a: L.Operand, W: torch.Tensor, *, w_sr: int, w_so: int, Kred: int, N: int, Ns: int, M: int,
+            Y: torch.Tensor, epi: int = EPI_STORE, stats: Optional[torch.Tensor] = None, out_img_stride: int = 0,
+            w_cls_stride: int = 0, E1=None, e1_img_stride: int = 0, E2=None, ebnp=None, egate=None, bias=None,
+            Y2=None, rows_per_sample: int = 0) -> None:
+    _require_cuda(W, Y)
+    d = L.GemmDesc()
+    d.a = a
+    d.W = _ptr(W); d.w_sr = w_sr; d.w_so = w_so; d.w_cls_stride = w_cls_stride
+    d.Kred = Kred; d.N = N; d.Ns = Ns; d.M = M
+    d.Y = _ptr(Y); d.out_img_stride = out_img_stride; d.epi = epi; d.stats = _ptr(stats)
+    d.E1 = _ptr(E1); d.e1_img_stride = e1_img_stride; d.E2 = _ptr(E2)
+    d.ebnp = _ptr(ebnp); d.egate = _ptr(egate); d.bias = _ptr(bias); d.Y2 = _ptr(Y2)
+    d.rows_per_sample = rows_per_sample
+    L.check(L.load().c3d_pw_gemm(C.byref(d), _stream()), "c3d_pw_gemm")
+
+
+def pw_wgrad(p: L.Operand, q: L.Operand, *, M: int, dW: torch.Tensor, dw_sn: int, dw_sk: int, N: int, K: int) -> None:
+    _require_cuda(dW)
+    d = L.WgradDesc()
+    d.p = p; d.q = q; d.M = M; d.dW = _ptr(dW); d.dw_sn = dw_sn; d.dw_sk = dw_sk; d.N = N; d.K = K
+    L.check(L.load().c3d_pw_wgrad(C.byref(d), _stream()), "c3d_pw_wgrad")
+
+
+def bn_finalize(stats: Optional[torch.Tensor], groups: int, count: int, bn: torch.nn.Module, C_: int, Cs: int,
+                training: bool) -> torch.Tensor:
+    """stats -> bnp float[4][Cs]; updates bn.running_* in training (nn.BatchNorm3d semantics)."""
+    bnp = torch.empty(4 * Cs, device=bn.weight.device, dtype=torch.float32)
+    L.check(L.load().c3d_bn_finalize(_ptr(stats), groups, count, _ptr(bn.weight), _ptr(bn.bias),
+                                     _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
+                                     bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
+                                     1 if training else 0, _ptr(bnp), _stream()), "c3d_bn_finalize")
+    return bnp
+
+
+def bn_se_finalize(stats: torch.Tensor, N: int, count_per_sample: int, bn: torch.nn.Module, se, C_: int, Cs: int,
+                   training: bool):
+    """BN_b finalize (+ SE gate when `se` is the SqueezeExcitation module).  Returns
+    (bnp, zhat_mean[N,Cs], hidden[N,R] | None, gate[N,Cs] | None)."""
+    dev = bn.weight.device
+    bnp = torch.empty(4 * Cs, device=dev, dtype=torch.float32)
+    zhat_mean = torch.empty(N, Cs, device=dev, dtype=torch.float32)
+    if se is not None:
+        w1, b1, w2, b2 = se.block[0].weight, se.block[0].bias, se.block[2].weight, se.block[2].bias
+        R = w1.shape[0]
+        hidden = torch.empty(N, R, device=dev, dtype=torch.float32)
+        gate = torch.empty(N, Cs, device=dev, dtype=torch.float32)
+    else:
+        w1 = b1 = w2 = b2 = hidden = gate = None
+        R = 0
+    L.check(L.load().c3d_bn_se_finalize(_ptr(stats), N, count_per_sample, _ptr(bn.weight), _ptr(bn.bias),
+                                        _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
+                                        bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
+                                        1 if training else 0, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), R,
+                                        _ptr(bnp), _ptr(zhat_mean), _ptr(hidden), _ptr(gate), _stream()),
+            "c3d_bn_se_finalize")
+    return bnp, zhat_mean, hidden, gate
+
+
+def bn_add_relu(A: torch.Tensor, bnpA: torch.Tensor, B: Optional[torch.Tensor], bnpB: Optional[torch.Tensor],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    Cs = A.shape[-1]
+    M = A.numel() // Cs
+    Y = torch.empty_like(A) if out is None else out
+    L.check(L.load().c3d_bn_add_relu(_ptr(A), _ptr(bnpA), _ptr(B), _ptr(bnpB), _ptr(Y), M, Cs, _stream()),
+            "c3d_bn_add_relu")
+    return Y
+
+
+def dw_conv_fwd(X: torch.Tensor, bnp_a: torch.Tensor, w: torch.Tensor, C_: int, stride: int,
+                stats: Optional[torch.Tensor]) -> torch.Tensor:
+    N, T, IH, IW, Cs = X.shape
+    OH, OW = (IH - 1) // stride + 1, (IW - 1) // stride + 1
+    Y = torch.empty(N, T, OH, OW, Cs, device=X.device, dtype=torch.float32)
+    L.check(L.load().c3d_dw_conv_fwd(_ptr(X), _ptr(bnp_a), _ptr(w), _ptr(Y), _ptr(stats), N, T, IH, IW, C_, Cs,
+                                     stride, _stream()), "c3d_dw_conv_fwd")
+    return Y
+
+
+def stem_fwd(frames, w_xy: torch.Tensor, w_t: torch.Tensor, B: int, H: int, W: int,
+             stats: Optional[torch.Tensor]) -> torch.Tensor:
+    """frames: list of T (tensor, stride_n, stride_c) — planes of H*W floats (see c3d_stem_fwd)."""
+    T = len(frames)
+    ptrs = (C.c_void_p * T)(*[f[0].data_ptr() for f in frames])
+    sn = (C.c_longlong * T)(*[f[1] for f in frames])
+    sc = (C.c_longlong * T)(*[f[2] for f in frames])
+    Y = torch.empty(B, T, H, W, 24, device=w_xy.device, dtype=torch.float32)
+    L.check(L.load().c3d_stem_fwd(ptrs, sn, sc, _ptr(w_xy), _ptr(w_t), _ptr(Y), _ptr(stats), B, T, H, W, _stream()),
+            "c3d_stem_fwd")
+    return Y
+
+
+def dec_head_fwd(X: torch.Tensor, w: torch.Tensor, apply_sigmoid: bool) -> torch.Tensor:
+    B, H, W, C_ = X.shape
+    ncls = w.shape[0]
+    Y = torch.empty(B, ncls, H, W, device=X.device, dtype=torch.float32)
+    L.check(L.load().c3d_dec_head_fwd(_ptr(X), _ptr(w), _ptr(Y), B, H, W, C_, ncls, 1 if apply_sigmoid else 0,
+                                      _stream()), "c3d_dec_head_fwd")
+    return Y
+
+
+# ---------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------
+def relu_bwd_stats(dOut, out, y_c, bnp_c, y_1, bnp_1, stats_c, stats_1) -> torch.Tensor:
+    Cs = dOut.shape[-1]
+    M = dOut.numel() // Cs
+    d_pre = torch.empty_like(dOut)
+    L.check(L.load().c3d_relu_bwd_stats(_ptr(dOut), _ptr(out), _ptr(y_c), _ptr(bnp_c), _ptr(y_1), _ptr(bnp_1),
+                                        _ptr(d_pre), _ptr(stats_c), _ptr(stats_1), M, Cs, _stream()),
+            "c3d_relu_bwd_stats")
+    return d_pre
+
+
+def bn_bwd_finalize(stats, groups: int, count: int, C_: int, Cs: int, dgamma: torch.Tensor, dbeta: torch.Tensor):
+    coef = torch.empty(2 * Cs, device=stats.device, dtype=torch.float32)
+    L.check(L.load().c3d_bn_bwd_finalize(_ptr(stats), groups, count, C_, Cs, _ptr(coef), _ptr(dgamma), _ptr(dbeta),
+                                         _stream()), "c3d_bn_bwd_finalize")
+    return coef
+
+
+def se_bn_bwd_finalize(stats, N: int, count_per_sample: int, bnp, bn, se, gate, hidden, zhat_mean, C_: int, Cs: int,
+                       dgamma, dbeta, se_grads):
+    dev = stats.device
+    coef = torch.empty(2 * Cs, device=dev, dtype=torch.float32)
+    if se is not None:
+        w1, w2 = se.block[0].weight, se.block[2].weight
+        R = w1.shape[0]
+        dpool = torch.empty(N, Cs, device=dev, dtype=torch.float32)
+        dw1, db1, dw2, db2 = se_grads
+    else:
+        w1 = w2 = dpool = dw1 = db1 = dw2 = db2 = None
+        gate = hidden = zhat_mean = None
+        R = 0
+    L.check(L.load().c3d_se_bn_bwd_finalize(_ptr(stats), N, count_per_sample, _ptr(bnp), _ptr(bn.weight), _ptr(bn.bias),
+                                            _ptr(gate), _ptr(hidden), _ptr(zhat_mean), _ptr(w1), _ptr(w2), C_, Cs, R,
+                                            _ptr(coef), _ptr(dgamma), _ptr(dbeta), _ptr(dpool), _ptr(dw1), _ptr(db1),
+                                            _ptr(dw2), _ptr(db2), _stream()), "c3d_se_bn_bwd_finalize")
+    return coef, dpool
+
+
+def dw_conv_bwd(du, y_b, bnp_b, gate, dpool, coef_b, y_a, bnp_a, w, C_: int, stride: int, stats_a, dW) -> torch.Tensor:
+    N, T, IH, IW, Cs = y_a.shape
+    dr = torch.empty_like(y_a)
+    L.check(L.load().c3d_dw_conv_bwd(_ptr(du), _ptr(y_b), _ptr(bnp_b), _ptr(gate), _ptr(dpool), _ptr(coef_b),
+                                     _ptr(y_a), _ptr(bnp_a), _ptr(w), _ptr(dr), _ptr(dW), _ptr(stats_a), N, T, IH, IW,
+                                     C_, Cs, stride, _stream()), "c3d_dw_conv_bwd")
+    return dr
+
+
+def colsum(X: torch.Tensor, out: torch.Tensor) -> None:
+    Cs = X.shape[-1]
+    L.check(L.load().c3d_colsum(_ptr(X), X.numel() // Cs, Cs, _ptr(out), _stream()), "c3d_colsum")
+
+
+def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc) -> None:
+    T = len(frames)
+    B, _, H, W, _ = y.shape
+    ptrs = (C.c_void_p * T)(*[f[0].data_ptr() for f in frames])
+    sn = (C.c_longlong * T)(*[f[1] for f in frames])
+    sc = (C.c_longlong * T)(*[f[2] for f in frames])
+    L.check(L.load().c3d_stem_bwd(ptrs, sn, sc, _ptr(d_pre), _ptr(y), _ptr(bnp), _ptr(coef), _ptr(w_xy), _ptr(w_t),
+                                  _ptr(dwxy), _ptr(dwt), _ptr(dperc), B, T, H, W, _stream()), "c3d_stem_bwd")
+
+
+def dec_head_bwd(dpred, pred, X, w, is_sigmoid: bool, dW) -> torch.Tensor:
+    B, H, W, C_ = X.shape
+    dX = torch.empty_like(X)
+    L.check(L.load().c3d_dec_head_bwd(_ptr(dpred), _ptr(pred), _ptr(X), _ptr(w), _ptr(dX), _ptr(dW), B, H, W, C_,
+                                      w.shape[0], 1 if is_sigmoid else 0, _stream()), "c3d_dec_head_bwd")
+    return dX
+
+
+def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
+              grad_scale: float = 1.0) -> None:
+    _require_cuda(p, g, m, v)
+    L.check(L.load().c3d_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                                   step, grad_scale, _stream()), "c3d_adam_step")

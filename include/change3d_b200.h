@@ -1,0 +1,193 @@
+/* change3d_b200 — C ABI of the B200-native X3D change-detection hot path.
+ *
+ * The reference (zhuduowang/Change3D) has no FFI/plugin layer: its hot path is torch.nn modules
+ * (model/x3d.py, model/change_decoder.py, model/trainer.py).  This header is the boundary a
+ * maintainer binds instead of those modules' forward/backward: plain device pointers + sizes,
+ * a cudaStream_t passed as void*, int status return (0 = ok, C3D_ERR_* otherwise), no C++
+ * exceptions, no torch types.  All tensors are fp32, activations NDHWC ([N,T,H,W,Cs], channel
+ * stride Cs a multiple of 4; pad lanes must be zero).  Every launch is stream-ordered and
+ * re-entrant across streams; buffers are borrowed for the duration of the launch only.
+ *
+ * Each entry cites the reference code it replaces.
+ */
+#ifndef CHANGE3D_B200_H
+#define CHANGE3D_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3D_ABI_VERSION 1
+
+/* status codes */
+#define C3D_STATUS_OK 0
+#define C3D_STATUS_BAD_ARGUMENT 1
+#define C3D_STATUS_CUDA_ERROR 2
+#define C3D_STATUS_SHARED_MEMORY 3
+
+int c3d_version(void);
+
+/* ---- operand of the pointwise-GEMM family --------------------------------------------------
+ * A GEMM row is one NDHWC pixel.  `mode` fuses a prologue into the global->shared staging:
+ *   0 none | 1 relu(bn(A)) | 2 swish(gate * bn(A)) | 3 BN-backward: scale*(A - c1 - yhat(A2)*c2)
+ *   | 4 |A - A2|
+ * `map` selects the row addressing:
+ *   0 dense (img_stride between images) | 1 stride-2 spatial subsample
+ *   | 2 ConvTranspose2d(k4,s2,p1) forward gather (K = 4*ld) | 3 its backward gather (K = 16*ld)
+ * bnp = float[4][ld] (mean, rstd, gamma*rstd, beta) from c3d_bn_finalize; coef = float[2][ld].
+ */
+typedef struct c3d_operand {
+  const float* A;
+  const float* A2;
+  const float* bnp;
+  const float* coef;
+  const float* gate;          /* [samples][ld] or NULL */
+  int mode, map;
+  int ld;                     /* channel stride of A / A2 */
+  int OH, OW;                 /* GEMM-row grid per image */
+  int IH, IW;                 /* source grid per image */
+  long long img_stride;       /* elements between images of A */
+  long long img_stride2;      /* ... of A2 (0 = same as A) */
+  int frames_per_sample;      /* gate row = image / frames_per_sample */
+  int seg0, nseg;             /* gather maps: stage taps [seg0, seg0+nseg) only (nseg 0 = all) */
+} c3d_operand;
+
+/* Y[M x Ns] = epilogue( prologue(A)[M x K] * Wt[K x N] ),  Wt[red][out] = W[cls*w_cls_stride + red*w_sr + out*w_so]
+ * epi: 0 store (+ per-channel sum / sum-of-squares into stats[2][Ns], double, atomically added)
+ *      1 Y += relu(acc) in place, previous Y saved to Y2                 (Encoder.enhance, model/trainer.py:88-108)
+ *      2 Swish/SE/BN_b backward: du = acc * swish'(gate*bn(E1)); stats[sample][2][Ns] += (du, du*yhat)
+ *      3 Y = acc + E1 (+ E2 upsampled x2 at even pixels)                 (residual / shortcut gradient join)
+ *      4 ConvTranspose2d scatter: Y[2j+py,2i+px] = acc + bias + E1       (model/change_decoder.py:30-45,71-73)
+ * Replaces nn.Conv3d 1x1x1 conv_a / conv_c / branch1_conv forward and dgrad (model/x3d.py:173-175,214-216,301-311)
+ * and the decoder / enhance 1x1 Conv2d. */
+typedef struct c3d_gemm_desc {
+  c3d_operand a;
+  const float* W;
+  long long w_sr, w_so, w_cls_stride;
+  int Kred;                   /* logical reduction length (0 = a's staged width) */
+  int N, Ns;                  /* logical / strided output channels */
+  long long M;                /* GEMM rows */
+  float* Y;
+  long long out_img_stride;   /* 0 = dense */
+  int epi;
+  double* stats;              /* may be NULL */
+  const float* E1;
+  long long e1_img_stride;
+  const float* E2;
+  const float* ebnp;
+  const float* egate;
+  const float* bias;
+  float* Y2;
+  long long rows_per_sample;  /* epi 2: rows per batch sample */
+} c3d_gemm_desc;
+
+int c3d_pw_gemm(const c3d_gemm_desc* desc, void* cuda_stream);
+
+/* dW[n*dw_sn + k*dw_sk] += sum_rows P[row][n] * Q[row][k]   (fp32 atomics; dW must be zeroed by the caller)
+ * Replaces the weight gradient of the same convolutions (autograd of model/x3d.py:173-175,214-216,301-311;
+ * model/change_decoder.py:30-45; model/trainer.py:57-69). */
+typedef struct c3d_wgrad_desc {
+  c3d_operand p, q;
+  long long M;
+  float* dW;
+  long long dw_sn, dw_sk;
+  int N, K;
+} c3d_wgrad_desc;
+
+int c3d_pw_wgrad(const c3d_wgrad_desc* desc, void* cuda_stream);
+
+/* ---- BatchNorm3d statistics -> parameter block -------------------------------------------------
+ * nn.BatchNorm3d(eps=1e-5, momentum=0.1) (model/x3d.py:94-98,176-180,203-208,217-221,296-298).
+ * stats = double[groups][2][Cs] (sum, sum of squares) accumulated by the producing kernel.
+ * training != 0: batch statistics, running stats updated in place (unbiased variance);
+ * training == 0: running statistics.  Writes bnp = float[4][Cs]; pad lanes (c >= C) are zeroed. */
+int c3d_bn_finalize(const double* stats, int groups, long long count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int C, int Cs, float momentum, float eps,
+                    int training, float* bnp, void* cuda_stream);
+
+/* BN_b finalize + SqueezeExcitation gate (fvcore SqueezeExcitation, call site model/x3d.py:194-202):
+ * stats = double[N][2][Cs] per-sample sums from c3d_dw_conv_fwd; gate[n][c] = sigmoid(W2 relu(W1 pooled + b1) + b2),
+ * pooled[n][c] = bn(mean_{T,H,W} y).  Saves zhat_mean[N][Cs], hidden[N][R], gate[N][Cs] for backward. */
+int c3d_bn_se_finalize(const double* stats, int N, long long count_per_sample, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, int C, int Cs, float momentum, float eps, int training,
+                       const float* w1, const float* b1, const float* w2, const float* b2, int R,
+                       float* bnp, float* zhat_mean, float* hidden, float* gate, void* cuda_stream);
+
+/* Y = relu( bnA(A) + [bnB(B) | B] ) elementwise over [M x Cs]; bnpB / B may be NULL.
+ * ResBlock fusion + activation (model/x3d.py:326-327) and the stem's BN+ReLU (model/x3d.py:94-99). */
+int c3d_bn_add_relu(const float* A, const float* bnpA, const float* B, const float* bnpB, float* Y,
+                    long long M, int Cs, void* cuda_stream);
+
+/* ---- depthwise 3x3x3 Conv3d (conv_b, model/x3d.py:184-193), stride (1,s,s), pad 1 --------------
+ * input = relu(bn_a(Xraw)) applied on the fly (zero padding in the activated domain).
+ * stats = double[N][2][Cs] per-sample (sum, sum of squares) of the raw output. w = torch layout [C][1][3][3][3]. */
+int c3d_dw_conv_fwd(const float* X, const float* bnp_a, const float* w, float* Y, double* stats,
+                    int N, int T, int IH, int IW, int C, int Cs, int stride, void* cuda_stream);
+
+/* ---- stem (model/x3d.py:23-106): frame assembly (model/trainer.py:154-162) + Conv3d 1x3x3 (3->24)
+ * + depthwise 5x1x1 temporal conv; raw output + BN statistics (double[2][24]).
+ * Frame f of sample n, channel ci is the H*W plane at frame_ptr[f] + n*stride_n[f] + ci*stride_c[f]
+ * (host arrays of T entries), so [pre, perception frames (stride_n = 0), post] is read in place.
+ * Y = [B][T][H][W][24], T in 3..5. w_xy = conv.conv_t.weight [24][3][1][3][3], w_t = conv.conv_xy.weight [24][1][5][1][1]. */
+int c3d_stem_fwd(const float* const* frame_ptr, const long long* stride_n, const long long* stride_c,
+                 const float* w_xy, const float* w_t, float* Y, double* stats, int B, int T, int H, int W,
+                 void* cuda_stream);
+
+/* ---- decoder head (model/change_decoder.py:53-55,76-79): Conv2d 3x3 (C -> ncls, pad 1, no bias) + optional sigmoid */
+int c3d_dec_head_fwd(const float* X, const float* w, float* Y, int B, int H, int W, int C, int ncls,
+                     int apply_sigmoid, void* cuda_stream);
+
+/* ============================== backward ============================== */
+
+/* ReLU backward of a ResBlock / stem output fused with the BN backward reductions of the layer(s) below:
+ * d_pre = dOut * (out > 0); stats_c[2][Cs] += (sum d_pre, sum d_pre*yhat_c); when the shortcut is normalised
+ * (branch1_norm, model/x3d.py:296-298,312) stats_1 likewise with y_1 / bnp_1.  (autograd of model/x3d.py:326-327) */
+int c3d_relu_bwd_stats(const float* dOut, const float* out, const float* y_c, const float* bnp_c, const float* y_1,
+                       const float* bnp_1, float* d_pre, double* stats_c, double* stats_1, long long M, int Cs,
+                       void* cuda_stream);
+
+/* BatchNorm backward coefficients: coef[2][Cs] = (mean d, mean d*yhat); dgamma = sum d*yhat; dbeta = sum d. */
+int c3d_bn_bwd_finalize(const double* stats, int groups, long long count, int C, int Cs, float* coef, float* dgamma,
+                        float* dbeta, void* cuda_stream);
+
+/* SqueezeExcitation backward (+ BN_b backward coefficients).  stats = double[N][2][Cs] per-sample (sum du, sum du*zhat)
+ * from c3d_pw_gemm epi 2.  gate == NULL: plain BN_b block.  Outputs coef[2][Cs], dgamma/dbeta[C], dpool[N][Cs]
+ * (= dL/dpooled / (T*H*W)), and the SE parameter gradients dw1[R][C], db1[R], dw2[C][R], db2[C]. */
+int c3d_se_bn_bwd_finalize(const double* stats, int N, long long count_per_sample, const float* bnp, const float* gamma,
+                           const float* beta, const float* gate, const float* hidden, const float* zhat_mean,
+                           const float* w1, const float* w2, int C, int Cs, int R, float* coef, float* dgamma,
+                           float* dbeta, float* dpool, float* dw1, float* db1, float* dw2, float* db2, void* cuda_stream);
+
+/* conv_b backward (autograd of model/x3d.py:184-193 with BN_b/SE on its output and ReLU+BN_a on its input):
+ * dy_b = scale_b*(du*gate + dpool - c1 - zhat*c2) on the fly; dr = conv_transpose(dy_b, w) * (bn_a(y_a) > 0);
+ * dW[C][27] += (fp32 atomics, caller zeroes); stats_a[2][Cs] += (sum dr, sum dr*yhat_a). */
+int c3d_dw_conv_bwd(const float* du, const float* y_b, const float* bnp_b, const float* gate, const float* dpool,
+                    const float* coef_b, const float* y_a, const float* bnp_a, const float* w, float* dr, float* dW,
+                    double* stats_a, int N, int T, int IH, int IW, int C, int Cs, int stride, void* cuda_stream);
+
+/* out[c] += sum_rows X[row][c]  (ConvTranspose2d bias gradient, model/change_decoder.py:32,38,44) */
+int c3d_colsum(const float* X, long long M, int Cs, float* out, void* cuda_stream);
+
+/* Stem backward (autograd of model/x3d.py:70-99 and of the frame assembly model/trainer.py:154-162).
+ * d_pre = gradient after the ReLU mask, y_raw = saved raw stem output, coef from c3d_bn_bwd_finalize.
+ * dw_xy[24][27], dw_t[24][5], dperception[3][P][H][W] are accumulated with fp32 atomics (caller zeroes);
+ * dperception may be NULL. */
+int c3d_stem_bwd(const float* const* frame_ptr, const long long* stride_n, const long long* stride_c,
+                 const float* d_pre, const float* y_raw, const float* bnp, const float* coef, const float* w_xy,
+                 const float* w_t, float* dw_xy, float* dw_t, float* dperception, int B, int T, int H, int W,
+                 void* cuda_stream);
+
+/* Decoder head backward (autograd of model/change_decoder.py:76-79): dpred/pred NCHW, X/dX NHWC, dW[ncls][C][3][3]
+ * accumulated with fp32 atomics (caller zeroes). */
+int c3d_dec_head_bwd(const float* dpred, const float* pred, const float* X, const float* w, float* dX, float* dW,
+                     int B, int H, int W, int C, int ncls, int is_sigmoid, void* cuda_stream);
+
+/* torch.optim.Adam step (scripts/train_BCD.py:284-290: L2 weight decay added to the gradient) on flat, 16-byte
+ * aligned fp32 buffers; g is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int c3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -153,7 +153,10 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int, dtype=torch.float3
         fan_in *= d
     if ".1.weight" in key and len(shape) == 4 and shape[-1] == 4:
         fan_in = shape[0] * 4        # ConvTranspose2d k4 s2: 4 taps reach each output pixel
-    return (torch.randn(shape, generator=g) * math.sqrt(2.0 / max(fan_in, 1))).to(dtype)
+    gain = 2.0
+    if "up_c1.0.weight" in key:
+        gain = 2.0 * 0.02 ** 2       # keep the head's logits O(1): saturated sigmoids make BCE gradients meaningless
+    return (torch.randn(shape, generator=g) * math.sqrt(gain / max(fan_in, 1))).to(dtype)
 
 
 def synth_state_dict(schema: Sequence[Tuple[str, Tuple[int, ...]]], seed: int, dtype=torch.float32) -> StateDict:
@@ -226,9 +229,10 @@ def res_block(sd: StateDict, p: str, x: Tensor, first: bool, has_se: bool, train
     return F.relu(sc + bottleneck(sd, p + "branch2.", x, 2 if first else 1, has_se, training))
 
 
-def res_stage(sd: StateDict, s: int, x: Tensor, training: bool, prefix: str = "") -> Tensor:
-    """model/x3d.py:331-412: `depth` blocks, stride on block 0 only, SE on even block indices."""
-    depth = STAGES[s - 1][3]
+def res_stage(sd: StateDict, s: int, x: Tensor, training: bool, prefix: str = "", depth: Optional[int] = None) -> Tensor:
+    """model/x3d.py:331-412: `depth` blocks, stride on block 0 only, SE on even block indices.
+    (`depth` override: tests run a truncated stage to keep fp32 round-off from compounding.)"""
+    depth = STAGES[s - 1][3] if depth is None else depth
     for b in range(depth):
         x = res_block(sd, f"{prefix}blocks.{s}.res_blocks.{b}.", x, b == 0, (b + 1) % 2 == 1, training)
     return x
