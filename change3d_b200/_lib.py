@@ -90,6 +90,10 @@ def load():
     return lib
 
 
+LAUNCHES = [0]      # kernels launched through the C ABI by this process (bench.py reports it)
+
+
 def check(status: int, what: str) -> None:
+    LAUNCHES[0] += 1
     if status != 0:
         raise RuntimeError(f"change3d_b200: {what} failed: {STATUS.get(status, status)}")

@@ -248,7 +248,14 @@ class GradArena:
     """One zero-filled fp32 buffer per backward call; every parameter gradient of the stage is a view
     into it (the wgrad kernels accumulate with atomics, so the memory must start at zero)."""
 
-    def __init__(self, params, device):
+    def __init__(self, params, device, direct=None):
+        self.i = 0
+        self.direct = direct is not None
+        if direct is not None:
+            # views into a persistent flat gradient buffer (change3d_b200.train_step): the kernels accumulate
+            # straight into it, autograd gets None for these parameters
+            self.views = direct
+            return
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]      # keep every view 16-byte aligned
         self.buf = torch.zeros(max(sum(sizes), 4), dtype=torch.float32, device=device)
         self.views = []
@@ -256,7 +263,10 @@ class GradArena:
         for p, n in zip(params, sizes):
             self.views.append(self.buf[off:off + p.numel()].view(p.shape))
             off += n
-        self.i = 0
+
+    def returned(self):
+        """What the autograd Function hands back for the parameters."""
+        return [None] * len(self.views) if self.direct else list(self.views)
 
     def next(self) -> torch.Tensor:
         v = self.views[self.i]
@@ -351,7 +361,7 @@ def res_stage_backward(stage, saved: List[BlockSaved], g: torch.Tensor):
     ResStage.param_list() order])."""
     N = g.shape[0]
     params = stage.param_list()
-    ga = GradArena(params, g.device)
+    ga = GradArena(params, g.device, getattr(stage, "_c3d_grad_views", None))
     total = 0
     for blk in stage.res_blocks:
         ci = blk.branch2.conv_a.weight.shape[0]
@@ -367,7 +377,7 @@ def res_stage_backward(stage, saved: List[BlockSaved], g: torch.Tensor):
         ga.i = starts[bi]
         g = res_block_backward(stage.res_blocks[bi], saved[bi], g, arena, ga)
         saved[bi] = None          # release this block's activations
-    return g, ga.views
+    return g, ga.returned()
 
 
 def enhance_backward(out: torch.Tensor, mid_pre: torch.Tensor, fc_w: torch.Tensor, P: int, g: torch.Tensor):
@@ -387,10 +397,11 @@ def enhance_backward(out: torch.Tensor, mid_pre: torch.Tensor, fc_w: torch.Tenso
                      img_stride2=H * W * Cc)
     ops.pw_gemm(de, fc_w, w_sr=Cc, w_so=1, Kred=Cc, N=Cc, Ns=Cc, M=M, Y=g[:, 0], Y2=g[:, P + 1], out_img_stride=fs,
                 epi=EPI_ABSDIFF_BWD, E1=x0, E2=x1, e1_img_stride=fs)
-    dfc = torch.zeros_like(fc_w)
+    direct = getattr(fc_w, "_c3d_grad_view", None)
+    dfc = direct if direct is not None else torch.zeros_like(fc_w)
     ops.pw_wgrad(de, absd, M=M, dW=dfc, dw_sn=Cc, dw_sk=1, N=Cc, K=Cc)
     out[:, mid].copy_(mid_pre)
-    return dfc
+    return None if direct is not None else dfc
 
 
 def stem_backward(stem, frames, y, bnp, out, g, P: int, want_dperc: bool = True):
@@ -399,13 +410,18 @@ def stem_backward(stem, frames, y, bnp, out, g, P: int, want_dperc: bool = True)
     B, T, H, W, _ = y.shape
     dev = y.device
     w_xy, w_t = stem.conv.conv_t.weight, stem.conv.conv_xy.weight
-    ga = GradArena([w_xy, w_t, stem.norm.weight, stem.norm.bias], dev)
+    ga = GradArena([w_xy, w_t, stem.norm.weight, stem.norm.bias], dev, getattr(stem, "_c3d_grad_views", None))
     dwxy, dwt, dgamma, dbeta = ga.views
     st = torch.zeros(48, dtype=torch.float64, device=dev)
     d_pre = ops.relu_bwd_stats(g, out, y, bnp, None, None, st, None)
     coef = ops.bn_bwd_finalize(st, 1, B * T * H * W, 24, 24, dgamma, dbeta)
-    dperc = torch.zeros(1, 3, P, H, W, device=dev, dtype=torch.float32) if want_dperc else None
+    dperc = None
+    perc_direct = getattr(stem, "_c3d_perc_grad_view", None) if want_dperc else None
+    if want_dperc:
+        dperc = perc_direct if perc_direct is not None else torch.zeros(1, 3, P, H, W, device=dev, dtype=torch.float32)
     ops.stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc)
+    if ga.direct:
+        return (None if perc_direct is not None else dperc), None, None, None, None
     return dperc, dwxy, dwt, dgamma, dbeta
 
 
@@ -448,7 +464,7 @@ def decoder_backward(dec, saved, g: torch.Tensor):
     """Backward of ChangeDecoder.forward.  g: (B,ncls,H,W) contiguous.  Returns ([d c1, d c2, d c3, d c4] as
     (B,C,H,W) views of NHWC tensors, [parameter grads in ChangeDecoder.param_list() order])."""
     params = dec.param_list()
-    ga = GradArena(params, g.device)
+    ga = GradArena(params, g.device, getattr(dec, "_c3d_grad_views", None))
     h4, w4 = saved["hw4"]
     c1f, c2f, c3f = saved["c1f"], saved["c2f"], saved["c3f"]
     c4, s4 = saved["c4"]
@@ -461,4 +477,4 @@ def decoder_backward(dec, saved, g: torch.Tensor):
     ga.i = 0
     d_c4 = decoder_up_backward(dec.up_c4, d_c3f, saved["t4"], c4, s4, h4, w4, ga)
     dfeats = [t.permute(0, 3, 1, 2) for t in (d_c1f, d_c2f, d_c3f, d_c4)]
-    return dfeats, ga.views
+    return dfeats, ga.returned()

@@ -20,6 +20,29 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+# Optional per-launch profiler used by bench.py's roofline probe: when PROF is a dict, every wrapper brackets its
+# launch with CUDA events on the launching stream and records (events, algorithmic bytes) under the kernel family.
+PROF = None
+
+
+class _Timed:
+    def __init__(self, family: str, nbytes: int):
+        self.family, self.nbytes = family, nbytes
+
+    def __enter__(self):
+        if PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROF is not None:
+            self.e1.record()
+            PROF.setdefault(self.family, []).append((self.e0, self.e1, self.nbytes))
+        return False
+
+
 def pad8(c: int) -> int:
     """Channel stride of the bottleneck's inner tensors (54->56, 108->112, 216, 432)."""
     return (c + 7) // 8 * 8
@@ -73,14 +96,20 @@ def pw_gemm(a: L.Operand, W: torch.Tensor, *, w_sr: int, w_so: int, Kred: int, N
     d.E1 = _ptr(E1); d.e1_img_stride = e1_img_stride; d.E2 = _ptr(E2)
     d.ebnp = _ptr(ebnp); d.egate = _ptr(egate); d.bias = _ptr(bias); d.Y2 = _ptr(Y2)
     d.rows_per_sample = rows_per_sample
-    L.check(L.load().c3d_pw_gemm(C.byref(d), _stream()), "c3d_pw_gemm")
+    ka = a.ld * (a.nseg if a.nseg else (4 if a.map == MAP_CONVT_FWD else 16 if a.map == MAP_CONVT_BWD else 1))
+    nbytes = 4 * (M * ka * (2 if a.A2 else 1) + M * Ns * (1 + (1 if E1 is not None else 0)) + Kred * N)
+    with _Timed("pw_gemm", nbytes):
+        L.check(L.load().c3d_pw_gemm(C.byref(d), _stream()), "c3d_pw_gemm")
 
 
 def pw_wgrad(p: L.Operand, q: L.Operand, *, M: int, dW: torch.Tensor, dw_sn: int, dw_sk: int, N: int, K: int) -> None:
     _require_cuda(dW)
     d = L.WgradDesc()
     d.p = p; d.q = q; d.M = M; d.dW = _ptr(dW); d.dw_sn = dw_sn; d.dw_sk = dw_sk; d.N = N; d.K = K
-    L.check(L.load().c3d_pw_wgrad(C.byref(d), _stream()), "c3d_pw_wgrad")
+    kq = q.ld * (q.nseg if q.nseg else (16 if q.map == MAP_CONVT_BWD else 1))
+    nbytes = 4 * (M * p.ld * (2 if p.A2 else 1) + M * kq * (2 if q.A2 else 1) + N * K)
+    with _Timed("pw_wgrad", nbytes):
+        L.check(L.load().c3d_pw_wgrad(C.byref(d), _stream()), "c3d_pw_wgrad")
 
 
 def bn_finalize(stats: Optional[torch.Tensor], groups: int, count: int, bn: torch.nn.Module, C_: int, Cs: int,
@@ -123,8 +152,9 @@ def bn_add_relu(A: torch.Tensor, bnpA: torch.Tensor, B: Optional[torch.Tensor], 
     Cs = A.shape[-1]
     M = A.numel() // Cs
     Y = torch.empty_like(A) if out is None else out
-    L.check(L.load().c3d_bn_add_relu(_ptr(A), _ptr(bnpA), _ptr(B), _ptr(bnpB), _ptr(Y), M, Cs, _stream()),
-            "c3d_bn_add_relu")
+    with _Timed("bn_add_relu", 4 * M * Cs * (3 if B is not None else 2)):
+        L.check(L.load().c3d_bn_add_relu(_ptr(A), _ptr(bnpA), _ptr(B), _ptr(bnpB), _ptr(Y), M, Cs, _stream()),
+                "c3d_bn_add_relu")
     return Y
 
 
@@ -133,8 +163,9 @@ def dw_conv_fwd(X: torch.Tensor, bnp_a: torch.Tensor, w: torch.Tensor, C_: int, 
     N, T, IH, IW, Cs = X.shape
     OH, OW = (IH - 1) // stride + 1, (IW - 1) // stride + 1
     Y = torch.empty(N, T, OH, OW, Cs, device=X.device, dtype=torch.float32)
-    L.check(L.load().c3d_dw_conv_fwd(_ptr(X), _ptr(bnp_a), _ptr(w), _ptr(Y), _ptr(stats), N, T, IH, IW, C_, Cs,
-                                     stride, _stream()), "c3d_dw_conv_fwd")
+    with _Timed("dw_conv_fwd", 4 * (X.numel() + Y.numel() + 27 * C_)):
+        L.check(L.load().c3d_dw_conv_fwd(_ptr(X), _ptr(bnp_a), _ptr(w), _ptr(Y), _ptr(stats), N, T, IH, IW, C_, Cs,
+                                         stride, _stream()), "c3d_dw_conv_fwd")
     return Y
 
 
@@ -146,8 +177,9 @@ def stem_fwd(frames, w_xy: torch.Tensor, w_t: torch.Tensor, B: int, H: int, W: i
     sn = (C.c_longlong * T)(*[f[1] for f in frames])
     sc = (C.c_longlong * T)(*[f[2] for f in frames])
     Y = torch.empty(B, T, H, W, 24, device=w_xy.device, dtype=torch.float32)
-    L.check(L.load().c3d_stem_fwd(ptrs, sn, sc, _ptr(w_xy), _ptr(w_t), _ptr(Y), _ptr(stats), B, T, H, W, _stream()),
-            "c3d_stem_fwd")
+    with _Timed("stem_fwd", 4 * (Y.numel() + B * T * 3 * H * W)):
+        L.check(L.load().c3d_stem_fwd(ptrs, sn, sc, _ptr(w_xy), _ptr(w_t), _ptr(Y), _ptr(stats), B, T, H, W,
+                                      _stream()), "c3d_stem_fwd")
     return Y
 
 
@@ -155,8 +187,9 @@ def dec_head_fwd(X: torch.Tensor, w: torch.Tensor, apply_sigmoid: bool) -> torch
     B, H, W, C_ = X.shape
     ncls = w.shape[0]
     Y = torch.empty(B, ncls, H, W, device=X.device, dtype=torch.float32)
-    L.check(L.load().c3d_dec_head_fwd(_ptr(X), _ptr(w), _ptr(Y), B, H, W, C_, ncls, 1 if apply_sigmoid else 0,
-                                      _stream()), "c3d_dec_head_fwd")
+    with _Timed("dec_head_fwd", 4 * (X.numel() + Y.numel())):
+        L.check(L.load().c3d_dec_head_fwd(_ptr(X), _ptr(w), _ptr(Y), B, H, W, C_, ncls, 1 if apply_sigmoid else 0,
+                                          _stream()), "c3d_dec_head_fwd")
     return Y
 
 
@@ -167,9 +200,10 @@ def relu_bwd_stats(dOut, out, y_c, bnp_c, y_1, bnp_1, stats_c, stats_1) -> torch
     Cs = dOut.shape[-1]
     M = dOut.numel() // Cs
     d_pre = torch.empty_like(dOut)
-    L.check(L.load().c3d_relu_bwd_stats(_ptr(dOut), _ptr(out), _ptr(y_c), _ptr(bnp_c), _ptr(y_1), _ptr(bnp_1),
-                                        _ptr(d_pre), _ptr(stats_c), _ptr(stats_1), M, Cs, _stream()),
-            "c3d_relu_bwd_stats")
+    with _Timed("relu_bwd_stats", 4 * M * Cs * (5 if y_1 is not None else 4)):
+        L.check(L.load().c3d_relu_bwd_stats(_ptr(dOut), _ptr(out), _ptr(y_c), _ptr(bnp_c), _ptr(y_1), _ptr(bnp_1),
+                                            _ptr(d_pre), _ptr(stats_c), _ptr(stats_1), M, Cs, _stream()),
+                "c3d_relu_bwd_stats")
     return d_pre
 
 
@@ -203,9 +237,10 @@ def se_bn_bwd_finalize(stats, N: int, count_per_sample: int, bnp, bn, se, gate, 
 def dw_conv_bwd(du, y_b, bnp_b, gate, dpool, coef_b, y_a, bnp_a, w, C_: int, stride: int, stats_a, dW) -> torch.Tensor:
     N, T, IH, IW, Cs = y_a.shape
     dr = torch.empty_like(y_a)
-    L.check(L.load().c3d_dw_conv_bwd(_ptr(du), _ptr(y_b), _ptr(bnp_b), _ptr(gate), _ptr(dpool), _ptr(coef_b),
+    with _Timed("dw_conv_bwd", 4 * (du.numel() + y_b.numel() + y_a.numel() + dr.numel())):
+      L.check(L.load().c3d_dw_conv_bwd(_ptr(du), _ptr(y_b), _ptr(bnp_b), _ptr(gate), _ptr(dpool), _ptr(coef_b),
                                      _ptr(y_a), _ptr(bnp_a), _ptr(w), _ptr(dr), _ptr(dW), _ptr(stats_a), N, T, IH, IW,
-                                     C_, Cs, stride, _stream()), "c3d_dw_conv_bwd")
+                                       C_, Cs, stride, _stream()), "c3d_dw_conv_bwd")
     return dr
 
 
@@ -220,14 +255,16 @@ def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc) -> None:
     ptrs = (C.c_void_p * T)(*[f[0].data_ptr() for f in frames])
     sn = (C.c_longlong * T)(*[f[1] for f in frames])
     sc = (C.c_longlong * T)(*[f[2] for f in frames])
-    L.check(L.load().c3d_stem_bwd(ptrs, sn, sc, _ptr(d_pre), _ptr(y), _ptr(bnp), _ptr(coef), _ptr(w_xy), _ptr(w_t),
+    with _Timed("stem_bwd", 4 * (2 * y.numel() + B * T * 3 * H * W)):
+      L.check(L.load().c3d_stem_bwd(ptrs, sn, sc, _ptr(d_pre), _ptr(y), _ptr(bnp), _ptr(coef), _ptr(w_xy), _ptr(w_t),
                                   _ptr(dwxy), _ptr(dwt), _ptr(dperc), B, T, H, W, _stream()), "c3d_stem_bwd")
 
 
 def dec_head_bwd(dpred, pred, X, w, is_sigmoid: bool, dW) -> torch.Tensor:
     B, H, W, C_ = X.shape
     dX = torch.empty_like(X)
-    L.check(L.load().c3d_dec_head_bwd(_ptr(dpred), _ptr(pred), _ptr(X), _ptr(w), _ptr(dX), _ptr(dW), B, H, W, C_,
+    with _Timed("dec_head_bwd", 4 * (2 * X.numel() + 2 * dpred.numel())):
+      L.check(L.load().c3d_dec_head_bwd(_ptr(dpred), _ptr(pred), _ptr(X), _ptr(w), _ptr(dX), _ptr(dW), B, H, W, C_,
                                       w.shape[0], 1 if is_sigmoid else 0, _stream()), "c3d_dec_head_bwd")
     return dX
 

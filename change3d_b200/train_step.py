@@ -1,0 +1,147 @@
+"""One training iteration of the reference loop (scripts/train_BCD.py:179-216) on the B200 engine.
+
+    output = model.update_bcd(pre, post); loss = BCEDiceLoss(output, target)
+    optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+with the reference's optimizer (torch.optim.Adam(lr, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-4),
+scripts/train_BCD.py:284-290) restated as ONE fused kernel over a flat parameter buffer:
+
+  * every parameter that the task trains becomes a view of one flat fp32 buffer; the wgrad kernels
+    accumulate straight into the matching views of a flat gradient buffer (one memset per step);
+  * parameters that never receive a gradient (blocks.4 / blocks.5 in BCD/SCD/BDA — torch's Adam skips
+    `grad is None`, scripts/train_BCD.py:284) are left out of the flat buffers, hence untouched;
+  * data parallel: one process per GPU, the flat gradient buffer is all-reduced once (NCCL, sum) and the
+    mean is folded into the Adam kernel (grad_scale = 1 / world_size); BatchNorm statistics stay per rank
+    (the reference uses plain nn.BatchNorm3d);
+  * the whole iteration can be captured in a CUDA graph (static shapes) to remove launch overhead.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .model.utils import BCEDiceLoss
+
+
+def _trained_parameters(model) -> List[torch.nn.Parameter]:
+    """Parameters that receive gradients on the change-decoder tasks: everything except x3d.blocks[4], blocks[5]
+    (never executed, model/trainer.py:127-139)."""
+    out = []
+    for name, p in model.named_parameters():
+        if ".x3d.blocks.4." in name or ".x3d.blocks.5." in name:
+            continue
+        if p.requires_grad:
+            out.append(p)
+    return out
+
+
+class FlatAdam:
+    """Flat-buffer Adam with the reference's hyper-parameters; gradients are written in place by the kernels."""
+
+    def __init__(self, model, lr: float = 2e-4, betas=(0.9, 0.99), eps: float = 1e-8, weight_decay: float = 1e-4):
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.params = _trained_parameters(model)
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        total = sum(sizes)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.step_count = 0
+        off = 0
+        gview = {}
+        for p, n in zip(self.params, sizes):
+            pv = self.flat_p[off:off + p.numel()].view(p.shape)
+            pv.copy_(p.data)
+            p.data = pv                                   # the module's parameter now lives in the flat buffer
+            gview[id(p)] = self.flat_g[off:off + p.numel()].view(p.shape)
+            off += n
+        self.numel = total
+        self._install(gview)
+
+    def _install(self, gview) -> None:
+        """Tell the engine where each module's parameter gradients live (see engine.GradArena)."""
+        m = self.model
+        enc = m.encoder
+        stem = enc.x3d.blocks[0]
+        object.__setattr__(stem, "_c3d_grad_views", [gview[id(p)] for p in (stem.conv.conv_t.weight,
+                                                                           stem.conv.conv_xy.weight,
+                                                                           stem.norm.weight, stem.norm.bias)])
+        object.__setattr__(stem, "_c3d_perc_grad_view", gview[id(enc.perception_frames)])
+        for i in range(1, 4):
+            stage = enc.x3d.blocks[i]
+            object.__setattr__(stage, "_c3d_grad_views", [gview[id(p)] for p in stage.param_list()])
+        for fc in enc.fc:
+            fc[0].weight._c3d_grad_view = gview[id(fc[0].weight)]
+        for name in ("decoder", "decoder_pre", "decoder_post", "decoder_change", "decoder_cls", "decoder_loc"):
+            dec = getattr(m, name, None)
+            if dec is not None and hasattr(dec, "param_list"):
+                object.__setattr__(dec, "_c3d_grad_views", [gview[id(p)] for p in dec.param_list()])
+
+    def zero_grad(self) -> None:
+        self.flat_g.zero_()
+
+    def all_reduce(self) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+
+    def step(self, lr: Optional[float] = None) -> None:
+        self.step_count += 1
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr if lr is None else lr, self.betas[0],
+                      self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / world)
+
+
+class BCDTrainStep:
+    """model.update_bcd -> BCEDiceLoss -> backward -> (all-reduce) -> fused Adam, optionally as a CUDA graph."""
+
+    def __init__(self, model, lr: float = 2e-4, use_graph: bool = False):
+        self.model = model.train()
+        self.opt = FlatAdam(model, lr=lr)
+        self.use_graph = use_graph
+        self.graph = None
+        self.static = None
+        self.loss = None
+
+    def _iteration(self, pre, post, target) -> torch.Tensor:
+        self.opt.zero_grad()
+        out = self.model.update_bcd(pre, post)
+        loss = BCEDiceLoss(out, target)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, pre: torch.Tensor, post: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None):
+        """pre/post (B,3,H,W), target (B,1,H,W) on the GPU.  Returns the (device) loss of this iteration."""
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if not self.use_graph:
+            loss = self._iteration(pre, post, target)
+            self.opt.all_reduce()
+            self.opt.step(lr)
+            return loss
+        if self.graph is None:
+            # warm-up on a side stream (also sets every kernel's shared-memory attribute), then capture
+            self.static = (pre.clone(), post.clone(), target.clone())
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._iteration(*self.static)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            from . import _lib
+            n0 = _lib.LAUNCHES[0]
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._iteration(*self.static)
+            self.captured_launches = _lib.LAUNCHES[0] - n0 + 1      # + the Adam launch outside the graph
+        for dst, src in zip(self.static, (pre, post, target)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.opt.all_reduce()
+        self.opt.step(lr)                 # Adam outside the graph: step count / lr change every iteration
+        return self.loss
