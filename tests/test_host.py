@@ -1,0 +1,143 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels run)."""
+import argparse
+import contextlib
+import io
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import change3d_oracle as O
+from oracle import reference_loader as R
+
+
+def _trainer(task, H, W, ncls):
+    from change3d_b200.model.trainer import Trainer
+    P = {"bcd": 1, "bda": 2, "scd": 3}[task]
+    a = argparse.Namespace(num_perception_frame=P, num_class=ncls, in_height=H, in_width=W,
+                           dataset={"bcd": "LEVIR-CD", "bda": "xBD", "scd": "SECOND"}[task], pretrained="/nonexistent")
+    with contextlib.redirect_stdout(io.StringIO()):
+        return Trainer(a)
+
+
+@pytest.mark.parametrize("task,ncls", [("bcd", 1), ("bda", 5), ("scd", 7)])
+def test_state_dict_schema_matches_reference(task, ncls):
+    """Same keys, order and shapes as the reference's Trainer -> checkpoints interchange."""
+    P = {"bcd": 1, "bda": 2, "scd": 3}[task]
+    m = _trainer(task, 32, 32, ncls)
+    schema = O.trainer_schema(task, P, 32, 32, ncls)
+    sd = m.state_dict()
+    assert list(sd.keys()) == [k for k, _ in schema]
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in schema)
+    m.load_state_dict(O.synth_state_dict(schema, 3), strict=True)
+    # parameters() order is what torch.optim.Adam and checkpointed optimizer state index by
+    assert [n for n, _ in m.named_parameters()] == [k for k, _ in schema if "running_" not in k and "num_batches" not in k]
+
+
+@pytest.mark.skipif(not R.available(), reason="reference tree not mounted")
+def test_matches_reference_modules_directly():
+    ref = R.build_trainer("bcd", 32, 32, 1)
+    mine = _trainer("bcd", 32, 32, 1)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict(), strict=True)      # reference checkpoint -> product
+    ref.load_state_dict(mine.state_dict(), strict=True)      # product checkpoint -> reference
+    # weight_init: same traversal and initialisers => identical tensors from the same RNG state
+    import model.utils as ref_utils   # the reference's file (path set up by reference_loader)
+    from change3d_b200.model.change_decoder import ChangeDecoder
+    from change3d_b200.model.utils import weight_init
+    a = argparse.Namespace(num_class=5)
+    torch.manual_seed(5)
+    d1 = ChangeDecoder(a, in_dim=[24, 24, 48, 96])
+    d2 = ChangeDecoder(a, in_dim=[24, 24, 48, 96])
+    d2.load_state_dict(d1.state_dict())
+    torch.manual_seed(7)
+    ref_utils.weight_init(d1)
+    torch.manual_seed(7)
+    weight_init(d2)
+    for (k1, v1), (k2, v2) in zip(d1.state_dict().items(), d2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+
+
+def test_param_lists_cover_every_trained_parameter():
+    m = _trainer("bcd", 32, 32, 1)
+    enc = m.encoder
+    ids = set()
+    stem = enc.x3d.blocks[0]
+    ids |= {id(p) for p in (stem.conv.conv_t.weight, stem.conv.conv_xy.weight, stem.norm.weight, stem.norm.bias)}
+    for i in range(1, 4):
+        pl = enc.x3d.blocks[i].param_list()
+        assert len(pl) == len(list(enc.x3d.blocks[i].parameters()))
+        assert [id(p) for p in pl] == [id(p) for p in enc.x3d.blocks[i].parameters()]   # registration order
+        ids |= {id(p) for p in pl}
+    ids |= {id(fc[0].weight) for fc in enc.fc} | {id(enc.perception_frames)} | {id(p) for p in m.decoder.param_list()}
+    from change3d_b200.train_step import _trained_parameters
+    trained = _trained_parameters(m)
+    assert {id(p) for p in trained} == ids
+    n = sum(p.numel() for p in trained) - enc.perception_frames.numel()
+    assert n == 1_542_656                                     # published BCD parameter count
+
+
+def test_flat_adam_buffers_on_cpu():
+    """FlatAdam re-homes the trained parameters into one flat buffer and installs gradient views (no CUDA needed)."""
+    from change3d_b200.train_step import FlatAdam
+    m = _trainer("bcd", 32, 32, 1)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    opt = FlatAdam(m)
+    after = m.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    p = m.encoder.x3d.blocks[2].res_blocks[3].branch2.conv_a.weight
+    assert p.data_ptr() >= opt.flat_p.data_ptr() and p.data_ptr() < opt.flat_p.data_ptr() + opt.flat_p.numel() * 4
+    gv = m.encoder.x3d.blocks[2]._c3d_grad_views
+    assert len(gv) == len(m.encoder.x3d.blocks[2].param_list())
+    gv[5].fill_(1.0)
+    assert opt.flat_g.sum().item() == gv[5].numel()
+    opt.zero_grad()
+    assert opt.flat_g.abs().sum().item() == 0
+    # blocks.4 / blocks.5 (never trained by BCD) stay outside the flat buffers
+    q = m.encoder.x3d.blocks[4].res_blocks[0].branch2.conv_a.weight
+    assert not (opt.flat_p.data_ptr() <= q.data_ptr() < opt.flat_p.data_ptr() + opt.flat_p.numel() * 4)
+
+
+def test_convtranspose_pack_index_reproduces_conv_transpose2d():
+    """The per-parity GEMM matrices built by engine.convt_pack_index, applied the way the kernel gathers
+    (output (2j+py, 2i+px) <- input rows {j, j-1} / {j+1, j}), equal F.conv_transpose2d(k=4, s=2, p=1)."""
+    from change3d_b200.engine import convt_pack_index
+    cin, cout, h, w = 5, 3, 4, 6
+    g = torch.Generator().manual_seed(0)
+    wt = torch.randn(cin, cout, 4, 4, generator=g)
+    x = torch.randn(1, cin, h, w, generator=g)
+    ref = F.conv_transpose2d(x, wt, None, stride=2, padding=1)
+    packed = wt.reshape(-1)[convt_pack_index(cin, cout, "cpu")].view(4, 4 * cin, cout)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros(1, cout, 2 * h, 2 * w)
+    for py in range(2):
+        for px in range(2):
+            rows = []
+            for ty in range(2):
+                for tx in range(2):
+                    dy = (0 if ty else 1) if py else (-1 if ty else 0)
+                    dx = (0 if tx else 1) if px else (-1 if tx else 0)
+                    rows.append(xp[0, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w])
+            a = torch.cat(rows, 0).permute(1, 2, 0).reshape(h * w, 4 * cin)
+            out[0, :, py::2, px::2] = (a @ packed[py * 2 + px]).t().reshape(cout, h, w)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_lr_schedule_matches_oracle():
+    from change3d_b200.model.utils import adjust_learning_rate
+    args = argparse.Namespace(lr_mode="poly", lr=2e-4, max_epochs=10, step_loss=None)
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    for epoch, it in ((0, 0), (0, 150), (0, 250), (3, 5000)):
+        lr = adjust_learning_rate(args, opt, epoch, it, 800)
+        assert abs(lr - O.poly_lr(2e-4, it, 8000, epoch)) < 1e-15
+        assert opt.param_groups[0]["lr"] == lr
+
+
+def test_round_helpers_and_depths():
+    from change3d_b200.model.x3d import create_x3d, round_repeats, round_width
+    assert [round_width(12, 2.0), round_width(24, 2.0, divisor=8), round_width(54, 0.0625)] == [24, 48, 8]
+    assert [round_repeats(r, 5.0) for r in (1, 2, 5, 3)] == [5, 10, 25, 15]
+    net = create_x3d(input_clip_length=3, depth_factor=5.0)
+    assert len(net.blocks) == 6
+    assert [len(net.blocks[i].res_blocks) for i in range(1, 5)] == [5, 10, 25, 15]
+    assert sum(p.numel() for p in net.parameters()) == 6_153_384
