@@ -23,7 +23,8 @@ enum { MAP_DENSE = 0, MAP_SUB2 = 1, MAP_CONVT_FWD = 2, MAP_CONVT_BWD = 3 };
 // GEMM epilogues
 enum { EPI_STORE = 0, EPI_RELU_ADD = 1, EPI_SWISH_BWD = 2, EPI_ADD2 = 3, EPI_CONVT = 4, EPI_ABSDIFF_BWD = 5 };
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// 1 / (1 + e^-v) with the SFU exponential and reciprocal (<= 2 ulp each; inf-safe: e^-v = inf -> 0)
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -6,24 +6,10 @@
 // Replaces (reference): nn.Conv3d 1x1x1 conv_a/conv_c/branch1_conv (model/x3d.py:173-175,214-216,
 // 301-311), Encoder.enhance's Conv2d (model/trainer.py:57-69,88-108), ChangeDecoder's Conv2d 1x1 and
 // ConvTranspose2d (model/change_decoder.py:30-45) and their autograd backward.
+#include <stdlib.h>
 #include "pw_gemm.cuh"
 #include "../../include/change3d_b200.h"
 
-struct GemmArgs {
-  TileSrc a;
-  const float* W; long long w_sr, w_so, w_cls_stride; int Kred;
-  int N, Ns; long long M;
-  float* Y; long long out_img_stride;
-  int epi;
-  double* stats;
-  const float* E1; long long e1_img_stride;
-  const float* E2;
-  const float* ebnp; const float* egate; const float* bias;
-  float* Y2;
-  long long rows_per_sample;
-  int NB;        // columns handled per CTA (multiple of 64)
-  int nsplit;    // grid.y = ncls * nsplit
-};
 
 template <int BM>
 __global__ void __launch_bounds__(256) pw_gemm_kernel(const GemmArgs g) {
@@ -312,6 +298,14 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const WgradArgs g) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+int c3d_launch_pw_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, int lbo_is_k);   // pw_gemm_tc.cu
+
+// C3D_TC=0 forces the FFMA inner product; C3D_TC_LBO=0 swaps the LBO/SBO descriptor convention (bring-up aid).
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -366,6 +360,11 @@ extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   g.ebnp = d->ebnp; g.egate = d->egate; g.bias = d->bias; g.Y2 = d->Y2;
   g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : (1LL << 62);
   const int ncls = d->epi == EPI_CONVT ? 4 : 1;
+  if (env_flag("C3D_TC", 1)) {
+    g.NB = 0; g.nsplit = 1;
+    const int r = c3d_launch_pw_gemm_tc(g, num_sms(), stream, env_flag("C3D_TC_LBO", 1));
+    if (r >= 0) return r;
+  }
 
   const int K = g.a.K;
   const int NBp = (d->Ns + 63) / 64 * 64;

@@ -4,6 +4,22 @@
 #pragma once
 #include "c3d_common.cuh"
 
+struct GemmArgs {
+  TileSrc a;
+  const float* W; long long w_sr, w_so, w_cls_stride; int Kred;
+  int N, Ns; long long M;
+  float* Y; long long out_img_stride;
+  int epi;
+  double* stats;
+  const float* E1; long long e1_img_stride;
+  const float* E2;
+  const float* ebnp; const float* egate; const float* bias;
+  float* Y2;
+  long long rows_per_sample;
+  int NB;        // columns handled per CTA (multiple of 64)
+  int nsplit;    // grid.y = ncls * nsplit
+};
+
 struct RowMeta {       // per tile row, in shared memory
   long long off;       // element offset of the row in A (dense / sub2 maps)
   long long off2;      // ... in A2

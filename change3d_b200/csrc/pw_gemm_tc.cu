@@ -1,0 +1,595 @@
+// tcgen05 inner product for the pointwise-GEMM family (sm_100a).
+//
+//   D[128 pixels x N] (fp32, TMEM) = A[128 x K] * B[K x N]        with fp32-class accuracy from a
+//   3-term TF32 split:  A = Ah + Al, B = Bh + Bl (h = top 19 bits, l = exact remainder),
+//   D += Ah*Bh + Al*Bh + Ah*Bl  (tcgen05.mma.kind::tf32, fp32 accumulate).
+//
+// Warp roles (one CTA per 128-pixel tile stream, persistent over a contiguous tile range):
+//   warps 0-7   epilogue, two warpgroups alternating tiles (even tiles -> warps 0-3 / accumulator set 0,
+//               odd tiles -> warps 4-7 / set 1): tcgen05.ld -> registers -> shared (row per thread) ->
+//               coalesced global stores, fused epilogue math (BN statistics / Swish'*SE*BN_b backward /
+//               residual join)
+//   warp  8     TMEM allocation + the single MMA-issuing thread
+//   warps 9-16  producers: global float4 loads of one 16-channel K-chunk of the tile, fused prologue
+//               (BN apply / ReLU / SE gate*Swish / BN-backward / |a-b| / mask), hi/lo split, stores in the
+//               UMMA canonical K-major (no-swizzle) layout, mbarrier arrive
+// The weight matrix (both split halves) stays resident in shared memory in the same canonical layout.
+// Each tile owns two TMEM accumulators: the main term Ah*Bh and the correction terms Al*Bh + Ah*Bl are
+// accumulated separately and added in the epilogue — the tensor core's fp32 accumulation rounds toward
+// zero, and keeping the 2^-11-sized terms out of the main chain cuts that bias ~3x.
+#include "pw_gemm.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;        // pixels per tile (UMMA M)
+constexpr int KC = 16;         // channels per pipeline stage (two K=8 tf32 MMA steps)
+constexpr int NPROD = 8;       // producer warps
+constexpr int NEPI = 8;        // epilogue warps (two warpgroups)
+constexpr int MMA_WARP = NEPI;
+constexpr int PROD_WARP0 = NEPI + 1;
+constexpr int NTHREADS = (NEPI + 1 + NPROD) * 32;
+constexpr int STAGE_FLOATS = BM * KC;          // per split half
+constexpr int EPI_LD = 36;                     // staging pitch (floats) of the epilogue tile: 32 columns + 4
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: element (row, k) of a [rows x K] tf32 tile lives at
+//   (k/4) * LBO + (row/8) * SBO + (row%8) * 16 + (k%4) * 4   bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (sm_100)
+  return d;                     // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// hi = x rounded to nearest TF32, lo = (x - hi) rounded to nearest TF32: both exactly representable, so the
+// tensor core's operand truncation is a no-op and the split error is unbiased (~2^-22 relative).
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = rna_tf32(x);
+  lo = rna_tf32(x - hi);
+}
+__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+struct Params {
+  GemmArgs g;
+  int NpB;           // accumulator width of this CTA (multiple of 16, <= 128)
+  int NpA;           // TMEM column stride per accumulator (multiple of 32, <= 128)
+  int tmem_cols;     // allocation: 4 accumulators (2 tile sets x {main, correction}), power of two >= 32
+  int nstage;        // pipeline stages == producer warps in use (each stage has exactly one producer warp, so
+                     // the parity-tracked empty/full mbarriers always see a single sequential producer)
+  int dense_contig;  // rows are contiguous pixels: offset = row * ld
+  int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
+  int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
+};
+
+// prologue applied to one float4 of 4 consecutive channels; per-channel parameters are passed in registers
+struct ChanParams { float4 mean, rstd, scale, beta, c1, c2; };
+
+template <int MODE>
+__device__ __forceinline__ ChanParams load_chan_params(const TileSrc& s, int c) {
+  ChanParams p;
+  p.mean = p.rstd = p.scale = p.beta = p.c1 = p.c2 = f4zero();
+  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH || MODE == PRO_BNBWD) {
+    p.mean = ldg4(BNP_MEAN(s.bnp, s.ld) + c);
+    p.scale = ldg4(BNP_SCALE(s.bnp, s.ld) + c);
+  }
+  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH) p.beta = ldg4(BNP_BETA(s.bnp, s.ld) + c);
+  if (MODE == PRO_BNBWD) {
+    p.rstd = ldg4(BNP_RSTD(s.bnp, s.ld) + c);
+    p.c1 = ldg4(s.coef + c);
+    p.c2 = ldg4(s.coef + s.ld + c);
+  }
+  return p;
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 prologue(const ChanParams& p, float4 v, float4 v2, float4 gate4) {
+  if (MODE == PRO_NONE) return v;
+  if (MODE == PRO_BN_RELU) return f4relu(f4bn(v, p.mean, p.scale, p.beta));
+  if (MODE == PRO_BN_GATE_SWISH) {
+    v = f4mul(f4bn(v, p.mean, p.scale, p.beta), gate4);
+    return make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+  }
+  if (MODE == PRO_BNBWD) {
+    v.x = p.scale.x * (v.x - p.c1.x - (v2.x - p.mean.x) * p.rstd.x * p.c2.x);
+    v.y = p.scale.y * (v.y - p.c1.y - (v2.y - p.mean.y) * p.rstd.y * p.c2.y);
+    v.z = p.scale.z * (v.z - p.c1.z - (v2.z - p.mean.z) * p.rstd.z * p.c2.z);
+    v.w = p.scale.w * (v.w - p.c1.w - (v2.w - p.mean.w) * p.rstd.w * p.c2.w);
+    return v;
+  }
+  if (MODE == PRO_ABSDIFF) return make_float4(fabsf(v.x - v2.x), fabsf(v.y - v2.y), fabsf(v.z - v2.z), fabsf(v.w - v2.w));
+  // PRO_MASK_POS
+  v.x = v2.x > 0.f ? v.x : 0.f; v.y = v2.y > 0.f ? v.y : 0.f; v.z = v2.z > 0.f ? v.z : 0.f; v.w = v2.w > 0.f ? v.w : 0.f;
+  return v;
+}
+
+// general row addressing (frame slices, stride-2 subsample): row -> element offsets of A / A2, image index
+__device__ __forceinline__ void row_offsets(const TileSrc& s, uint32_t row, long long& off, long long& off2, uint32_t& img) {
+  img = row / (uint32_t)s.OHW;
+  const uint32_t rem = row - img * (uint32_t)s.OHW;
+  const uint32_t oh = rem / (uint32_t)s.OW, ow = rem - oh * (uint32_t)s.OW;
+  const int mul = (s.map == MAP_SUB2) ? 2 : 1;
+  const long long pix = (long long)(oh * mul) * s.IW + ow * mul;
+  off = (long long)img * s.img_stride + pix * s.ld;
+  off2 = (long long)img * s.img_stride2 + pix * s.ld;
+}
+
+// One producer warp fills one stage: 128 rows x 16 channels, lane = (row % 8, 16-byte chunk), 16 row groups.
+template <int MODE>
+__device__ __forceinline__ void produce_chunk(const Params& P, const TileSrc& s, long long row0, int chunk, float* a_hi,
+                                              float* a_lo, int lane) {
+  constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
+  constexpr int BATCH = 8;
+  const int qq = lane >> 3, rl = lane & 7;
+  const int k = chunk * KC + 4 * qq;
+  const bool kvalid = k < s.K;
+  const long long M = P.g.M;
+  const bool fast = P.dense_contig && (row0 + BM <= M);
+  float* dst_hi = a_hi + (qq * 16 * 8 + rl) * 4;
+  float* dst_lo = a_lo + (qq * 16 * 8 + rl) * 4;
+  if (!kvalid) {      // K % 16 == 8: the upper half of the last chunk is never read by the MMA
+    return;
+  }
+  const ChanParams cp = load_chan_params<MODE>(s, k);
+  // SE gate: rows of a tile belong to at most two consecutive samples when a sample has >= 128 rows
+  float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+  int gsplit = BM;          // first tile row that belongs to the second sample
+  bool gate_fast = false;
+  if (MODE == PRO_BN_GATE_SWISH && s.gate && fast) {
+    const uint32_t rps = (uint32_t)s.OHW * (uint32_t)s.frames_per_sample;
+    if (rps >= (uint32_t)BM) {
+      const uint32_t samp0 = (uint32_t)row0 / rps;
+      gsplit = (int)((samp0 + 1) * rps - (uint32_t)row0);
+      g0 = ldg4(s.gate + (long long)samp0 * s.ld + k);
+      if (gsplit < BM) g1 = ldg4(s.gate + (long long)(samp0 + 1) * s.ld + k);
+      gate_fast = true;
+    }
+  }
+  const float* baseA = s.A + row0 * s.ld + k;
+  const float* baseA2 = HAS2 ? s.A2 + row0 * s.ld + k : nullptr;
+#pragma unroll 1
+  for (int b0 = 0; b0 < 16; b0 += BATCH) {
+    float4 v[BATCH], v2[BATCH];
+    uint32_t imgs[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int r = (b0 + i) * 8 + rl;
+      v2[i] = f4zero();
+      imgs[i] = 0;
+      if (fast) {
+        v[i] = ldg4(baseA + r * s.ld);
+        if (HAS2) v2[i] = ldg4(baseA2 + r * s.ld);
+      } else {
+        v[i] = f4zero();
+        const long long row = row0 + r;
+        if (row < M) {
+          long long off, off2;
+          if (P.dense_contig) { off = row * s.ld; off2 = off; imgs[i] = (uint32_t)row / (uint32_t)s.OHW; }
+          else row_offsets(s, (uint32_t)row, off, off2, imgs[i]);
+          v[i] = ldg4(s.A + off + k);
+          if (HAS2) v2[i] = ldg4(s.A2 + off2 + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int r = (b0 + i) * 8 + rl;
+      float4 x;
+      if (fast) {
+        float4 g4 = g0;
+        if (MODE == PRO_BN_GATE_SWISH && s.gate) {
+          if (gate_fast) g4 = (r >= gsplit) ? g1 : g0;
+          else g4 = ldg4(s.gate + (long long)(((uint32_t)(row0 + r) / (uint32_t)s.OHW) / (uint32_t)s.frames_per_sample) * s.ld + k);
+        }
+        x = prologue<MODE>(cp, v[i], v2[i], g4);
+      } else {
+        x = f4zero();
+        if (row0 + r < M) {
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (MODE == PRO_BN_GATE_SWISH && s.gate) g4 = ldg4(s.gate + (long long)(imgs[i] / (uint32_t)s.frames_per_sample) * s.ld + k);
+          x = prologue<MODE>(cp, v[i], v2[i], g4);
+        }
+      }
+      float4 hi, lo;
+      split4(x, hi, lo);
+      *reinterpret_cast<float4*>(dst_hi + (b0 + i) * 32) = hi;
+      *reinterpret_cast<float4*>(dst_lo + (b0 + i) * 32) = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const GemmArgs& g = P.g;
+  TileSrc a = g.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * P.NpB;
+  const int K = a.K;                      // multiple of 8
+  const int NpB = P.NpB;
+  const int nchunks = (K + KC - 1) / KC;
+
+  // ---- shared memory carve-up ----
+  float* B_hi = reinterpret_cast<float*>(smem_raw);                 // [K/4][NpB/8][8][4]
+  float* B_lo = B_hi + (size_t)NpB * K;
+  float* stages = B_lo + (size_t)NpB * K;                           // nstage x (A_hi, A_lo)
+  float* epi = stages + (size_t)P.nstage * 2 * STAGE_FLOATS;        // NEPI warps x epi_bufs x [32][EPI_LD]
+  float* s_stat = epi + NEPI * P.epi_bufs * 32 * EPI_LD;            // [NEPI warps][2][NpA]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + NEPI * 2 * P.NpA);
+  uint64_t* full = bars;                  // [nstage]
+  uint64_t* empty = bars + P.nstage;      // [nstage]
+  uint64_t* tfull = empty + P.nstage;     // [2]  accumulator set ready for its epilogue warpgroup
+  uint64_t* tempty = tfull + 2;           // [2]  accumulator set drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nstage; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  // resident weights, split and laid out for UMMA (zero outside the logical matrix)
+  {
+    const int kq4 = K >> 2;
+    const float* Wg = g.W;
+    for (int idx = threadIdx.x; idx < NpB * kq4; idx += NTHREADS) {
+      int n, q;
+      if (g.w_sr == 1) { n = idx / kq4; q = idx - n * kq4; } else { q = idx / NpB; n = idx - q * NpB; }
+      float w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int red = 4 * q + j;
+        w[j] = (red < g.Kred && n0 + n < g.N) ? __ldg(Wg + (long long)red * g.w_sr + (long long)(n0 + n) * g.w_so) : 0.f;
+      }
+      float4 hi, lo;
+      split4(make_float4(w[0], w[1], w[2], w[3]), hi, lo);
+      const int o = ((q * (NpB >> 3) + (n >> 3)) * 8 + (n & 7)) * 4;
+      *reinterpret_cast<float4*>(B_hi + o) = hi;
+      *reinterpret_cast<float4*>(B_lo + o) = lo;
+    }
+    for (int i = threadIdx.x; i < NEPI * 2 * P.NpA; i += NTHREADS) s_stat[i] = 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long ntiles = (g.M + BM - 1) / BM;
+  const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * tpc;
+  const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
+  const long long my_tiles = t_end > t_begin ? t_end - t_begin : 0;
+
+  if (warp >= PROD_WARP0) {
+    // ===================== producers =====================
+    const int p = warp - PROD_WARP0;
+    const long long total = (p < P.nstage) ? my_tiles * nchunks : 0;
+    uint32_t use = 0;
+    for (long long c = p; c < total; c += P.nstage, ++use) {
+      const long long ti = c / nchunks;
+      const int chunk = (int)(c - ti * nchunks);
+      mbar_wait(smem_u32(empty + p), (use & 1) ^ 1);
+      float* a_hi = stages + (size_t)p * 2 * STAGE_FLOATS;
+      float* a_lo = a_hi + STAGE_FLOATS;
+      const long long row0 = (t_begin + ti) * BM;
+      switch (a.mode) {
+        case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+        case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+        case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+        case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+        case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+        default: produce_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(full + p));
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NpB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t lboA = 16 * 128, sboA = 128;                       // stage layout [k-chunk][row group][8][16 B]
+      const uint32_t lboB = (uint32_t)(NpB >> 3) * 128, sboB = 128;     // weights     [k-chunk][col group][8][16 B]
+      const uint32_t bhi = smem_u32(B_hi), blo = smem_u32(B_lo);
+      long long c = 0;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        const int set = (int)(ti & 1);
+        mbar_wait(smem_u32(tempty + set), ((uint32_t)(ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * P.NpA);
+        const uint32_t d_corr = d_main + (uint32_t)P.NpA;
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++c) {
+          const int stage = (int)(c % P.nstage);
+          mbar_wait(smem_u32(full + stage), (uint32_t)(c / P.nstage) & 1);
+          tc_fence_after();
+          const uint32_t ahi = smem_u32(stages + (size_t)stage * 2 * STAGE_FLOATS), alo = ahi + STAGE_FLOATS * 4;
+          const int ksteps = (K - chunk * KC) >= KC ? 2 : 1;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t aoff = (uint32_t)ks * 2 * lboA, boff = (uint32_t)(chunk * 4 + ks * 2) * lboB;
+            uint64_t dah, dal, dbh, dbl;
+            if (P.lbo_is_k) {
+              dah = make_desc(ahi + aoff, lboA, sboA); dal = make_desc(alo + aoff, lboA, sboA);
+              dbh = make_desc(bhi + boff, lboB, sboB); dbl = make_desc(blo + boff, lboB, sboB);
+            } else {
+              dah = make_desc(ahi + aoff, sboA, lboA); dal = make_desc(alo + aoff, sboA, lboA);
+              dbh = make_desc(bhi + boff, sboB, lboB); dbl = make_desc(blo + boff, sboB, lboB);
+            }
+            const uint32_t first = (chunk == 0 && ks == 0) ? 0u : 1u;
+            umma_tf32(d_main, dah, dbh, idesc, first);
+            umma_tf32(d_corr, dal, dbh, idesc, first);
+            umma_tf32(d_corr, dah, dbl, idesc, 1u);
+          }
+          umma_commit(smem_u32(empty + stage));
+        }
+        umma_commit(smem_u32(tfull + set));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: warpgroup `set` (warps 4*set .. 4*set+3) handles tiles ti % 2 == set ===========
+    const int set = warp >> 2, wq = warp & 3;            // wq = TMEM lane quarter this warp may read
+    float* S = epi + (size_t)warp * P.epi_bufs * 32 * EPI_LD;
+    float* S2 = S + 32 * EPI_LD;      // only valid when P.epi_bufs == 2
+    float* st = s_stat + (size_t)warp * 2 * P.NpA;
+    const bool has_stats = g.stats != nullptr;
+    const int ncc = (NpB + 31) / 32;
+    const int bar_id = 1 + set;
+    long long cur_samp = -1;
+    auto flush = [&](long long samp) {
+      // the four warps of this warpgroup add their partial sums into the global statistics of `samp`
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const float* wg = s_stat + (size_t)(set * 4) * 2 * P.NpA;
+      for (int cidx = (threadIdx.x & 127); cidx < NpB; cidx += 128) {
+        if (n0 + cidx < g.Ns) {
+          float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { t1 += wg[(w * 2 + 0) * P.NpA + cidx]; t2 += wg[(w * 2 + 1) * P.NpA + cidx]; }
+          atomicAdd(g.stats + (samp * 2 + 0) * g.Ns + n0 + cidx, (double)t1);
+          atomicAdd(g.stats + (samp * 2 + 1) * g.Ns + n0 + cidx, (double)t2);
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      for (int i = lane; i < 2 * P.NpA; i += 32) st[i] = 0.f;
+      __syncwarp();
+    };
+    for (long long ti = set; ti < my_tiles; ti += 2) {
+      const long long row0 = (t_begin + ti) * BM;
+      const long long last = row0 + BM - 1 < g.M - 1 ? row0 + BM - 1 : g.M - 1;
+      const long long samp0 = row0 / g.rows_per_sample;
+      const bool straddle = (last / g.rows_per_sample) != samp0;
+      const bool full_tile = (row0 + BM <= g.M);
+      if (has_stats && samp0 != cur_samp) {
+        if (cur_samp >= 0) flush(cur_samp);
+        cur_samp = samp0;
+      }
+      mbar_wait(smem_u32(tfull + set), (uint32_t)(ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * 2 * P.NpA);
+      const uint32_t t_corr = t_main + (uint32_t)P.NpA;
+      for (int cc = 0; cc < ncc; ++cc) {
+        {
+          float r[32], r2[32];
+          tmem_ld32(t_main + (uint32_t)(cc * 32), r);
+          tmem_ld32(t_corr + (uint32_t)(cc * 32), r2);
+          if (cc == ncc - 1) {     // both accumulators fully read by this warp: hand the set back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty + set));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(S + lane * EPI_LD + 4 * j) =
+                make_float4(r[4 * j] + r2[4 * j], r[4 * j + 1] + r2[4 * j + 1], r[4 * j + 2] + r2[4 * j + 2], r[4 * j + 3] + r2[4 * j + 3]);
+        }
+        __syncwarp();
+        // coalesced pass: 8 lanes cover the 32 columns of a row, 4 rows per instruction
+        const int q = lane & 7;
+        const int cl = cc * 32 + 4 * q;          // column inside this CTA's accumulator
+        const int col = n0 + cl;
+        const bool col_ok = col < g.Ns && cl < NpB;
+        const long long tile_o = (row0 + wq * 32 + (lane >> 3)) * (long long)g.Ns + col;
+        if (g.epi == EPI_STORE) {
+          if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              if (full_tile || row0 + wq * 32 + rr < g.M)
+                st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, *reinterpret_cast<const float4*>(S + rr * EPI_LD + 4 * q));
+            }
+          }
+          __syncwarp();
+          if (has_stats) {     // column sums straight from the staged tile (rows past M and pad columns hold zeros)
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) { const float x = S[rr * EPI_LD + lane]; t1 += x; t2 = fmaf(x, x, t2); }
+            st[cc * 32 + lane] += t1;
+            st[P.NpA + cc * 32 + lane] += t2;
+          }
+        } else {
+          float4 mean = f4zero(), rstd = f4zero(), scale = f4zero(), beta = f4zero();
+          if (g.epi == EPI_SWISH_BWD && col_ok) {
+            mean = ldg4(BNP_MEAN(g.ebnp, g.Ns) + col); rstd = ldg4(BNP_RSTD(g.ebnp, g.Ns) + col);
+            scale = ldg4(BNP_SCALE(g.ebnp, g.Ns) + col); beta = ldg4(BNP_BETA(g.ebnp, g.Ns) + col);
+          }
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const long long row = row0 + wq * 32 + rr;
+            float4 v = *reinterpret_cast<const float4*>(S + rr * EPI_LD + 4 * q);
+            float4 v2 = f4zero();
+            if (row < g.M && col_ok) {
+              const long long o = tile_o + (long long)(4 * i) * g.Ns;
+              if (g.epi == EPI_SWISH_BWD) {
+                const float4 yb = ldg4(g.E1 + o);
+                const long long sp = row / g.rows_per_sample;
+                float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (g.egate) gt = ldg4(g.egate + sp * g.Ns + col);
+                float yv[4] = {yb.x, yb.y, yb.z, yb.w}, mv[4] = {mean.x, mean.y, mean.z, mean.w};
+                float rv[4] = {rstd.x, rstd.y, rstd.z, rstd.w}, sv[4] = {scale.x, scale.y, scale.z, scale.w};
+                float bv[4] = {beta.x, beta.y, beta.z, beta.w}, gv[4] = {gt.x, gt.y, gt.z, gt.w};
+                float av[4] = {v.x, v.y, v.z, v.w}, du[4], dz[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float xc = yv[j] - mv[j];
+                  const float zh = xc * rv[j];
+                  const float u = fmaf(xc, sv[j], bv[j]) * gv[j];
+                  du[j] = av[j] * swish_gradf_(u);
+                  dz[j] = du[j] * zh;
+                  if (straddle && has_stats) {
+                    atomicAdd(g.stats + (sp * 2 + 0) * g.Ns + col + j, (double)du[j]);
+                    atomicAdd(g.stats + (sp * 2 + 1) * g.Ns + col + j, (double)dz[j]);
+                  }
+                }
+                v = make_float4(du[0], du[1], du[2], du[3]);
+                v2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+                st4(g.Y + o, v);
+              } else {   // EPI_ADD2
+                if (g.E1) v = f4add(v, ldg4(g.E1 + o));
+                if (g.E2) {
+                  const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
+                  const uint32_t rem = (uint32_t)row - img * (uint32_t)a.OHW;
+                  const uint32_t oh = rem / (uint32_t)a.OW, ow = rem - oh * (uint32_t)a.OW;
+                  if (!(oh & 1) && !(ow & 1)) {
+                    const long long hr = (long long)img * (a.OHW >> 2) + (long long)(oh >> 1) * (a.OW >> 1) + (ow >> 1);
+                    v = f4add(v, ldg4(g.E2 + hr * g.Ns + col));
+                  }
+                }
+                st4(g.Y + o, v);
+              }
+            } else {
+              v = f4zero();
+            }
+            if (has_stats) {
+              *reinterpret_cast<float4*>(S + rr * EPI_LD + 4 * q) = v;
+              *reinterpret_cast<float4*>(S2 + rr * EPI_LD + 4 * q) = v2;
+            }
+          }
+          __syncwarp();
+          if (has_stats && !straddle) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) { t1 += S[rr * EPI_LD + lane]; t2 += S2[rr * EPI_LD + lane]; }
+            st[cc * 32 + lane] += t1;
+            st[P.NpA + cc * 32 + lane] += t2;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (has_stats && cur_samp >= 0) flush(cur_samp);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+}  // namespace tc
+
+// Host-side eligibility + launch.  Returns -1 when the shape / mode is not handled here (caller falls back
+// to the FFMA kernel), otherwise a C3D status.
+int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, int lbo_is_k) {
+  const GemmArgs& g = g0;
+  if (g.a.map != MAP_DENSE && g.a.map != MAP_SUB2) return -1;
+  if (g.epi != EPI_STORE && g.epi != EPI_SWISH_BWD && g.epi != EPI_ADD2) return -1;
+  if (g.out_img_stride != (long long)g.a.OHW * g.Ns) return -1;
+  if ((g.a.K & 7) || g.a.K < 8 || (g.Ns & 3)) return -1;
+  if (g.M >= (1LL << 31) || g.M < tc::BM) return -1;
+  if (g.M * (long long)(g.a.ld > g.Ns ? g.a.ld : g.Ns) >= (1LL << 40)) return -1;
+  tc::Params P;
+  P.g = g;
+  P.lbo_is_k = lbo_is_k;
+  const int K = g.a.K;
+  const int Np = (g.Ns + 15) / 16 * 16;
+  // split N across grid.y: <= 128 accumulator columns per CTA (4 TMEM accumulators of <= 128 columns) and the
+  // resident weights (both halves) must fit next to >= 3 pipeline stages
+  const size_t budget = 224 * 1024;
+  P.epi_bufs = (g.epi == EPI_SWISH_BWD && g.stats) ? 2 : 1;
+  int nsplit = 1, NpB = Np;
+  size_t fixed = 0;
+  for (;; ++nsplit) {
+    NpB = ((Np / 16 + nsplit - 1) / nsplit) * 16;
+    const int NpA = (NpB + 31) / 32 * 32;
+    if (NpA > 128) continue;
+    fixed = (size_t)2 * NpB * K * 4 + (size_t)tc::NEPI * P.epi_bufs * 32 * tc::EPI_LD * 4 + (size_t)tc::NEPI * 2 * NpA * 4 + 256;
+    if (fixed + (size_t)4 * 2 * tc::STAGE_FLOATS * 4 <= budget) break;
+    if (NpB <= 16) return -1;
+  }
+  nsplit = (Np + NpB - 1) / NpB;
+  P.NpB = NpB;
+  P.NpA = (NpB + 31) / 32 * 32;
+  int cols = 32;
+  while (cols < 4 * P.NpA) cols <<= 1;
+  P.tmem_cols = cols;
+  int nstage = (int)((budget - fixed) / ((size_t)2 * tc::STAGE_FLOATS * 4));
+  if (nstage > tc::NPROD) nstage = tc::NPROD;
+  P.nstage = nstage;
+  P.dense_contig = (g.a.map == MAP_DENSE && g.a.img_stride == (long long)g.a.OHW * g.a.ld &&
+                    (g.a.A2 == nullptr || g.a.img_stride2 == (long long)g.a.OHW * g.a.ld)) ? 1 : 0;
+  const size_t smem = fixed + (size_t)nstage * 2 * tc::STAGE_FLOATS * 4;
+  cudaError_t e = cudaFuncSetAttribute(tc::pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return C3D_ERR_SMEM;
+  const long long ntiles = (g.M + tc::BM - 1) / tc::BM;
+  long long gx = num_sms / nsplit;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  dim3 grid((unsigned)gx, (unsigned)nsplit);
+  tc::pw_gemm_tc_kernel<<<grid, tc::NTHREADS, smem, stream>>>(P);
+  return c3d_check_last(cudaGetLastError());
+}

@@ -57,6 +57,10 @@ def test_res_stage_backward(stage, depth, T, H, W, B):
     torch.cuda.synchronize()
     tag = f"stage{stage} depth{depth or full_depth} T{T}"
     check_vs_noise(tag + " dx", xg.grad, dx64, dx32)
+    # Full-depth stages: which near-zero activation flips its ReLU mask differs between any two fp32
+    # implementations, so a tensor torch happens to get to 4e-6 can be 1e-3 off here and vice versa.  The
+    # yardstick for those runs is the chain's own fp32 noise (torch fp32 vs fp64 on dx), not the per-tensor one.
+    chain_noise = rel_err(dx32, dx64) if depth is None else 0.0
     gmax = max(v.grad.abs().max().item() for k, v in g64.items() if v.grad is not None)
     worst, bad = 0.0, []
     for name, p in net.blocks[stage].named_parameters():
@@ -68,7 +72,7 @@ def test_res_stage_backward(stage, depth, T, H, W, B):
             continue
         e_mine, e_ref = rel_err(p.grad, ref64), rel_err(ref32, ref64)
         worst = max(worst, e_mine)
-        if e_mine > max(4.0 * e_ref, 2e-5):
+        if e_mine > max(4.0 * max(e_ref, chain_noise), 2e-5):
             bad.append((name, e_mine, e_ref))
             log(f"  BAD {tag} grad {name}: mine {e_mine:.3e} torch-fp32 {e_ref:.3e}")
     log(f"{tag}: worst parameter-gradient error {worst:.3e}, {len(bad)} outside 4x the fp32 noise")

@@ -43,10 +43,11 @@ def test_pw_gemm_forward_with_stats(cin, cout, M):
     ops.pw_gemm(ops.operand(xs, ld=cins, OH=1, OW=M), w.to(DEV), w_sr=1, w_so=cin, Kred=cin, N=cout, Ns=couts, M=M,
                 Y=y, stats=stats)
     torch.cuda.synchronize()
-    check(f"pw_gemm {cin}->{cout}", y[:, :cout], ref, 2e-6)
+    # tcgen05 path: 3-term TF32 split with fp32 accumulation (fp32-class: ~2^-21 per product)
+    check(f"pw_gemm {cin}->{cout}", y[:, :cout], ref, 3e-6)
     assert torch.all(y[:, cout:] == 0), "pad lanes must be zero"
-    check(f"pw_gemm {cin}->{cout} sum", stats[:cout], ref.sum(0), 2e-6)
-    check(f"pw_gemm {cin}->{cout} sumsq", stats[couts:couts + cout], (ref * ref).sum(0), 2e-6)
+    check(f"pw_gemm {cin}->{cout} sum", stats[:cout], ref.sum(0), 3e-6)
+    check(f"pw_gemm {cin}->{cout} sumsq", stats[couts:couts + cout], (ref * ref).sum(0), 3e-6)
 
 
 @pytest.mark.parametrize("T,stride,C,H,W,N", [(3, 1, 54, 12, 20, 2), (3, 2, 54, 16, 12, 2), (4, 1, 108, 8, 8, 1),
