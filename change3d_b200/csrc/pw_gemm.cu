@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const WgradArgs g) {
 // host side
 // ------------------------------------------------------------------------------------------
 int c3d_launch_pw_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, int lbo_is_k);   // pw_gemm_tc.cu
+int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
+                           int N, int K, int num_sms, cudaStream_t stream, int desc_swap);          // pw_wgrad_tc.cu
 
 // C3D_TC=0 forces the FFMA inner product; C3D_TC_LBO=0 swaps the LBO/SBO descriptor convention (bring-up aid).
 static int env_flag(const char* name, int dflt) {
@@ -362,7 +364,7 @@ extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   const int ncls = d->epi == EPI_CONVT ? 4 : 1;
   if (env_flag("C3D_TC", 1)) {
     g.NB = 0; g.nsplit = 1;
-    const int r = c3d_launch_pw_gemm_tc(g, num_sms(), stream, env_flag("C3D_TC_LBO", 1));
+    const int r = c3d_launch_pw_gemm_tc(g, num_sms(), stream, env_flag("C3D_TC_LBO", 1) | (env_flag("C3D_TC_HINT", 0) << 1));
     if (r >= 0) return r;
   }
 
@@ -438,6 +440,11 @@ extern "C" int c3d_pw_wgrad(const c3d_wgrad_desc* d, void* stream_) {
   fill_src(g.p, d->p);
   fill_src(g.q, d->q);
   g.M = d->M; g.dW = d->dW; g.dw_sn = d->dw_sn; g.dw_sk = d->dw_sk; g.N = d->N; g.K = d->K;
+  if (env_flag("C3D_TC", 1) && env_flag("C3D_TC_WGRAD", 1)) {
+    const int r = c3d_launch_pw_wgrad_tc(g.p, g.q, g.M, g.dW, g.dw_sn, g.dw_sk, g.N, g.K, num_sms(), stream,
+                                         env_flag("C3D_TC_WSWAP", 0));
+    if (r >= 0) return r;
+  }
   const int np = g.p.K, kq = g.q.K;
   const bool k1 = kq <= 64;
   if (np <= 32) return k1 ? launch_wgrad<2, 1>(g, stream) : launch_wgrad<2, 2>(g, stream);

@@ -19,6 +19,8 @@
 // zero, and keeping the 2^-11-sized terms out of the main chain cuts that bias ~3x.
 #include "pw_gemm.cuh"
 
+#include "tc_common.cuh"
+
 namespace tc {
 
 constexpr int BM = 128;        // pixels per tile (UMMA M)
@@ -31,78 +33,6 @@ constexpr int NTHREADS = (NEPI + 1 + NPROD) * 32;
 constexpr int STAGE_FLOATS = BM * KC;          // per split half
 constexpr int EPI_LD = 36;                     // staging pitch (floats) of the epilogue tile: 32 columns + 4
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(r);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, no swizzle: element (row, k) of a [rows x K] tf32 tile lives at
-//   (k/4) * LBO + (row/8) * SBO + (row%8) * 16 + (k%4) * 4   bytes.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;      // descriptor version (sm_100)
-  return d;                     // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
-}
-
-// hi = x rounded to nearest TF32, lo = (x - hi) rounded to nearest TF32: both exactly representable, so the
-// tensor core's operand truncation is a no-op and the split error is unbiased (~2^-22 relative).
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = rna_tf32(x);
-  lo = rna_tf32(x - hi);
-}
-__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
-  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-}
-
 struct Params {
   GemmArgs g;
   int NpB;           // accumulator width of this CTA (multiple of 16, <= 128)
@@ -112,60 +42,9 @@ struct Params {
                      // the parity-tracked empty/full mbarriers always see a single sequential producer)
   int dense_contig;  // rows are contiguous pixels: offset = row * ld
   int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
+  int wait_hint;     // mbarrier try_wait suspend hint in ns (0 = none)
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
 };
-
-// prologue applied to one float4 of 4 consecutive channels; per-channel parameters are passed in registers
-struct ChanParams { float4 mean, rstd, scale, beta, c1, c2; };
-
-template <int MODE>
-__device__ __forceinline__ ChanParams load_chan_params(const TileSrc& s, int c) {
-  ChanParams p;
-  p.mean = p.rstd = p.scale = p.beta = p.c1 = p.c2 = f4zero();
-  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH || MODE == PRO_BNBWD) {
-    p.mean = ldg4(BNP_MEAN(s.bnp, s.ld) + c);
-    p.scale = ldg4(BNP_SCALE(s.bnp, s.ld) + c);
-  }
-  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH) p.beta = ldg4(BNP_BETA(s.bnp, s.ld) + c);
-  if (MODE == PRO_BNBWD) {
-    p.rstd = ldg4(BNP_RSTD(s.bnp, s.ld) + c);
-    p.c1 = ldg4(s.coef + c);
-    p.c2 = ldg4(s.coef + s.ld + c);
-  }
-  return p;
-}
-
-template <int MODE>
-__device__ __forceinline__ float4 prologue(const ChanParams& p, float4 v, float4 v2, float4 gate4) {
-  if (MODE == PRO_NONE) return v;
-  if (MODE == PRO_BN_RELU) return f4relu(f4bn(v, p.mean, p.scale, p.beta));
-  if (MODE == PRO_BN_GATE_SWISH) {
-    v = f4mul(f4bn(v, p.mean, p.scale, p.beta), gate4);
-    return make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
-  }
-  if (MODE == PRO_BNBWD) {
-    v.x = p.scale.x * (v.x - p.c1.x - (v2.x - p.mean.x) * p.rstd.x * p.c2.x);
-    v.y = p.scale.y * (v.y - p.c1.y - (v2.y - p.mean.y) * p.rstd.y * p.c2.y);
-    v.z = p.scale.z * (v.z - p.c1.z - (v2.z - p.mean.z) * p.rstd.z * p.c2.z);
-    v.w = p.scale.w * (v.w - p.c1.w - (v2.w - p.mean.w) * p.rstd.w * p.c2.w);
-    return v;
-  }
-  if (MODE == PRO_ABSDIFF) return make_float4(fabsf(v.x - v2.x), fabsf(v.y - v2.y), fabsf(v.z - v2.z), fabsf(v.w - v2.w));
-  // PRO_MASK_POS
-  v.x = v2.x > 0.f ? v.x : 0.f; v.y = v2.y > 0.f ? v.y : 0.f; v.z = v2.z > 0.f ? v.z : 0.f; v.w = v2.w > 0.f ? v.w : 0.f;
-  return v;
-}
-
-// general row addressing (frame slices, stride-2 subsample): row -> element offsets of A / A2, image index
-__device__ __forceinline__ void row_offsets(const TileSrc& s, uint32_t row, long long& off, long long& off2, uint32_t& img) {
-  img = row / (uint32_t)s.OHW;
-  const uint32_t rem = row - img * (uint32_t)s.OHW;
-  const uint32_t oh = rem / (uint32_t)s.OW, ow = rem - oh * (uint32_t)s.OW;
-  const int mul = (s.map == MAP_SUB2) ? 2 : 1;
-  const long long pix = (long long)(oh * mul) * s.IW + ow * mul;
-  off = (long long)img * s.img_stride + pix * s.ld;
-  off2 = (long long)img * s.img_stride2 + pix * s.ld;
-}
 
 // One producer warp fills one stage: 128 rows x 16 channels, lane = (row % 8, 16-byte chunk), 16 row groups.
 template <int MODE>
@@ -322,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
     for (long long c = p; c < total; c += P.nstage, ++use) {
       const long long ti = c / nchunks;
       const int chunk = (int)(c - ti * nchunks);
-      mbar_wait(smem_u32(empty + p), (use & 1) ^ 1);
+      mbar_wait(smem_u32(empty + p), (use & 1) ^ 1, (uint32_t)P.wait_hint);
       float* a_hi = stages + (size_t)p * 2 * STAGE_FLOATS;
       float* a_lo = a_hi + STAGE_FLOATS;
       const long long row0 = (t_begin + ti) * BM;
@@ -348,13 +227,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
       long long c = 0;
       for (long long ti = 0; ti < my_tiles; ++ti) {
         const int set = (int)(ti & 1);
-        mbar_wait(smem_u32(tempty + set), ((uint32_t)(ti >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(tempty + set), ((uint32_t)(ti >> 1) & 1) ^ 1, (uint32_t)P.wait_hint);
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * P.NpA);
         const uint32_t d_corr = d_main + (uint32_t)P.NpA;
         for (int chunk = 0; chunk < nchunks; ++chunk, ++c) {
           const int stage = (int)(c % P.nstage);
-          mbar_wait(smem_u32(full + stage), (uint32_t)(c / P.nstage) & 1);
+          mbar_wait(smem_u32(full + stage), (uint32_t)(c / P.nstage) & 1, (uint32_t)P.wait_hint);
           tc_fence_after();
           const uint32_t ahi = smem_u32(stages + (size_t)stage * 2 * STAGE_FLOATS), alo = ahi + STAGE_FLOATS * 4;
           const int ksteps = (K - chunk * KC) >= KC ? 2 : 1;
@@ -416,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
         if (cur_samp >= 0) flush(cur_samp);
         cur_samp = samp0;
       }
-      mbar_wait(smem_u32(tfull + set), (uint32_t)(ti >> 1) & 1);
+      mbar_wait(smem_u32(tfull + set), (uint32_t)(ti >> 1) & 1, (uint32_t)P.wait_hint);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * 2 * P.NpA);
       const uint32_t t_corr = t_main + (uint32_t)P.NpA;
@@ -554,7 +433,8 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   if (g.M * (long long)(g.a.ld > g.Ns ? g.a.ld : g.Ns) >= (1LL << 40)) return -1;
   tc::Params P;
   P.g = g;
-  P.lbo_is_k = lbo_is_k;
+  P.lbo_is_k = lbo_is_k & 1;
+  P.wait_hint = lbo_is_k >> 1;      // upper bits of the bring-up flag carry the wait hint (C3D_TC_HINT)
   const int K = g.a.K;
   const int Np = (g.Ns + 15) / 16 * 16;
   // split N across grid.y: <= 128 accumulator columns per CTA (4 TMEM accumulators of <= 128 columns) and the

@@ -1,0 +1,142 @@
+// Shared pieces of the tcgen05 kernels (pointwise GEMM and weight gradient): PTX wrappers for mbarrier / TMEM /
+// tcgen05.mma, the round-to-nearest TF32 hi/lo split, and the fused operand prologues.
+#pragma once
+#include "pw_gemm.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Wait for the phase with the given parity.  `hint_ns` > 0 lets the hardware suspend the thread for up to that
+// long per probe (fewer issue slots burnt by spinning, but the wake-up can lag by as much); 0 = plain try_wait.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 0) {
+  uint32_t done;
+  if (hint_ns) {
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!done);
+  } else {
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: element (row, k) of a [rows x K] tf32 tile lives at
+//   (k/4) * LBO + (row/8) * SBO + (row%8) * 16 + (k%4) * 4   bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (sm_100)
+  return d;                     // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+// hi = x rounded to nearest TF32, lo = (x - hi) rounded to nearest TF32: both exactly representable, so the
+// tensor core's operand truncation is a no-op and the split error is unbiased (~2^-22 relative).
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = rna_tf32(x);
+  lo = rna_tf32(x - hi);
+}
+__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+// prologue applied to one float4 of 4 consecutive channels; per-channel parameters are passed in registers
+struct ChanParams { float4 mean, rstd, scale, beta, c1, c2; };
+
+template <int MODE>
+__device__ __forceinline__ ChanParams load_chan_params(const TileSrc& s, int c) {
+  ChanParams p;
+  p.mean = p.rstd = p.scale = p.beta = p.c1 = p.c2 = f4zero();
+  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH || MODE == PRO_BNBWD) {
+    p.mean = ldg4(BNP_MEAN(s.bnp, s.ld) + c);
+    p.scale = ldg4(BNP_SCALE(s.bnp, s.ld) + c);
+  }
+  if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH) p.beta = ldg4(BNP_BETA(s.bnp, s.ld) + c);
+  if (MODE == PRO_BNBWD) {
+    p.rstd = ldg4(BNP_RSTD(s.bnp, s.ld) + c);
+    p.c1 = ldg4(s.coef + c);
+    p.c2 = ldg4(s.coef + s.ld + c);
+  }
+  return p;
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 prologue(const ChanParams& p, float4 v, float4 v2, float4 gate4) {
+  if (MODE == PRO_NONE) return v;
+  if (MODE == PRO_BN_RELU) return f4relu(f4bn(v, p.mean, p.scale, p.beta));
+  if (MODE == PRO_BN_GATE_SWISH) {
+    v = f4mul(f4bn(v, p.mean, p.scale, p.beta), gate4);
+    return make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+  }
+  if (MODE == PRO_BNBWD) {
+    v.x = p.scale.x * (v.x - p.c1.x - (v2.x - p.mean.x) * p.rstd.x * p.c2.x);
+    v.y = p.scale.y * (v.y - p.c1.y - (v2.y - p.mean.y) * p.rstd.y * p.c2.y);
+    v.z = p.scale.z * (v.z - p.c1.z - (v2.z - p.mean.z) * p.rstd.z * p.c2.z);
+    v.w = p.scale.w * (v.w - p.c1.w - (v2.w - p.mean.w) * p.rstd.w * p.c2.w);
+    return v;
+  }
+  if (MODE == PRO_ABSDIFF) return make_float4(fabsf(v.x - v2.x), fabsf(v.y - v2.y), fabsf(v.z - v2.z), fabsf(v.w - v2.w));
+  // PRO_MASK_POS
+  v.x = v2.x > 0.f ? v.x : 0.f; v.y = v2.y > 0.f ? v.y : 0.f; v.z = v2.z > 0.f ? v.z : 0.f; v.w = v2.w > 0.f ? v.w : 0.f;
+  return v;
+}
+
+// general row addressing (frame slices, stride-2 subsample): row -> element offsets of A / A2, image index
+__device__ __forceinline__ void row_offsets(const TileSrc& s, uint32_t row, long long& off, long long& off2, uint32_t& img) {
+  img = row / (uint32_t)s.OHW;
+  const uint32_t rem = row - img * (uint32_t)s.OHW;
+  const uint32_t oh = rem / (uint32_t)s.OW, ow = rem - oh * (uint32_t)s.OW;
+  const int mul = (s.map == MAP_SUB2) ? 2 : 1;
+  const long long pix = (long long)(oh * mul) * s.IW + ow * mul;
+  off = (long long)img * s.img_stride + pix * s.ld;
+  off2 = (long long)img * s.img_stride2 + pix * s.ld;
+}
+
+
+}  // namespace tc

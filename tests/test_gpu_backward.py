@@ -20,6 +20,25 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.mark.parametrize("n,k,M", [(24, 54, 4096), (54, 24, 5000), (96, 216, 3000), (216, 96, 4096), (48, 108, 1000),
+                                    (24, 24, 2000)])
+def test_pw_wgrad(n, k, M):
+    """dW[n][k] = sum_rows P[row][n] * Q[row][k] (tcgen05 path: pixels are the MMA K dimension) vs fp64."""
+    from change3d_b200 import ops
+    from tests.gpu_util import pad_c
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    ns, ks = ops.pad8(n), ops.pad8(k)
+    P = torch.randn(M, n, generator=g)
+    Q = torch.randn(M, k, generator=g)
+    ref = P.double().t() @ Q.double()
+    Pd, Qd = pad_c(P, ns).to(DEV), pad_c(Q, ks).to(DEV)
+    dW = torch.zeros(n, k, device=DEV)
+    ops.pw_wgrad(ops.operand(Pd, ld=ns, OH=1, OW=M), ops.operand(Qd, ld=ks, OH=1, OW=M), M=M, dW=dW, dw_sn=k, dw_sk=1,
+                 N=n, K=k)
+    torch.cuda.synchronize()
+    check(f"pw_wgrad {n}x{k} M{M}", dW, ref, 3e-6)
+
+
 def _stage_grads(stage, x, wgt, sd, dtype, depth):
     osd = O.clone_sd(sd, dtype=dtype, requires_grad=True)
     xr = x.detach().clone().to(dtype).requires_grad_(True)
