@@ -25,11 +25,9 @@ namespace tc {
 
 constexpr int BM = 128;        // pixels per tile (UMMA M)
 constexpr int KC = 16;         // channels per pipeline stage (two K=8 tf32 MMA steps)
-constexpr int NPROD = 8;       // producer warps
-constexpr int NEPI = 8;        // epilogue warps (two warpgroups)
-constexpr int MMA_WARP = NEPI;
-constexpr int PROD_WARP0 = NEPI + 1;
-constexpr int NTHREADS = (NEPI + 1 + NPROD) * 32;
+// Role counts are template parameters: <8,8> (17 warps, one CTA per SM) or the compact <4,4> (9 warps) that fits
+// two CTAs per SM for the small-channel layers — per-tile latency (producer -> MMA -> commit -> epilogue hand-offs,
+// ~2 us) is what bounds these short-K GEMMs, so tiles in flight per SM matter more than anything else.
 constexpr int STAGE_FLOATS = BM * KC;          // per split half
 constexpr int EPI_LD = 36;                     // staging pitch (floats) of the epilogue tile: 32 columns + 4
 
@@ -38,8 +36,11 @@ struct Params {
   int NpB;           // accumulator width of this CTA (multiple of 16, <= 128)
   int NpA;           // TMEM column stride per accumulator (multiple of 32, <= 128)
   int tmem_cols;     // allocation: 4 accumulators (2 tile sets x {main, correction}), power of two >= 32
-  int nstage;        // pipeline stages == producer warps in use (each stage has exactly one producer warp, so
-                     // the parity-tracked empty/full mbarriers always see a single sequential producer)
+  int nstage;        // pipeline stages; stage s belongs to producer warp s % nprod (exactly one producer per stage,
+                     // so the parity-tracked empty/full mbarriers always see a single sequential producer)
+  int nprod;         // producer warps in use (<= NPROD, <= nstage)
+  int tma;           // 1: the raw operand rows arrive by TMA into the stage itself (64B-swizzled) and the
+                     // producer warps transform them in place; 0: producers gather rows with global loads
   int dense_contig;  // rows are contiguous pixels: offset = row * ld
   int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
   int wait_hint;     // mbarrier try_wait suspend hint in ns (0 = none)
@@ -130,8 +131,61 @@ __device__ __forceinline__ void produce_chunk(const Params& P, const TileSrc& s,
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// TMA path: the stage already holds the raw rows (A in the hi buffer, the second operand in the lo buffer), as
+// 128 rows x 64 bytes with the 16-byte units of row r XOR-swizzled by (r >> 1) & 3.  Apply the prologue and the
+// hi/lo split in place; a lane keeps its logical channel quad for all rows, so the physical offset inside an
+// 8-row group is a per-lane constant and a warp touches each 512-byte group exactly once (conflict-free).
+template <int MODE>
+__device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& s, long long row0, int chunk, float* a_hi,
+                                                float* a_lo, int lane) {
+  constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
+  const int qq = lane >> 3, rl = lane & 7;
+  const int k = chunk * KC + 4 * qq;
+  if (k >= s.K) return;      // K % 16 == 8: the upper half of the last chunk is never read by the MMA
+  const ChanParams cp = load_chan_params<MODE>(s, k);
+  float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+  int gsplit = BM;
+  bool gate_fast = true;
+  if (MODE == PRO_BN_GATE_SWISH && s.gate) {
+    const uint32_t rps = (uint32_t)s.OHW * (uint32_t)s.frames_per_sample;
+    if (rps >= (uint32_t)BM) {
+      const uint32_t samp0 = (uint32_t)row0 / rps;
+      gsplit = (int)((samp0 + 1) * rps - (uint32_t)row0);
+      g0 = ldg4(s.gate + (long long)samp0 * s.ld + k);
+      if (gsplit < BM && (long long)(samp0 + 1) * rps < P.g.M) g1 = ldg4(s.gate + (long long)(samp0 + 1) * s.ld + k);
+    } else {
+      gate_fast = false;
+    }
+  }
+  const long long left = P.g.M - row0;
+  const int nvalid = left < BM ? (int)left : BM;
+  const int po = rl * 16 + ((qq ^ ((rl >> 1) & 3)) << 2);
+#pragma unroll 4
+  for (int b = 0; b < 16; ++b) {
+    const int r = b * 8 + rl;
+    float4* ph = reinterpret_cast<float4*>(a_hi + b * 128 + po);
+    float4* pl = reinterpret_cast<float4*>(a_lo + b * 128 + po);
+    const float4 v = *ph;
+    const float4 v2 = HAS2 ? *pl : f4zero();
+    float4 g4 = (r >= gsplit) ? g1 : g0;
+    if (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast && r < nvalid)
+      g4 = ldg4(s.gate + (long long)(((uint32_t)(row0 + r) / (uint32_t)s.OHW) / (uint32_t)s.frames_per_sample) * s.ld + k);
+    float4 x = prologue<MODE>(cp, v, v2, g4);
+    if (r >= nvalid) x = f4zero();     // TMA zero-fills rows past M; keep them zero through the prologue
+    float4 hi, lo;
+    split4(x, hi, lo);
+    *ph = hi;
+    *pl = lo;
+  }
+}
+
+template <int NEPI, int NPROD>
+__global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) pw_gemm_tc_kernel(const Params P, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2) {
+  constexpr int MMA_WARP = NEPI;
+  constexpr int PROD_WARP0 = NEPI + 1;
+  constexpr int NTHREADS = (NEPI + 1 + NPROD) * 32;
+  constexpr int NWG = NEPI / 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const GemmArgs& g = P.g;
   TileSrc a = g.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,13 +203,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + NEPI * 2 * P.NpA);
   uint64_t* full = bars;                  // [nstage]
   uint64_t* empty = bars + P.nstage;      // [nstage]
-  uint64_t* tfull = empty + P.nstage;     // [2]  accumulator set ready for its epilogue warpgroup
+  uint64_t* rawfull = empty + P.nstage;   // [nstage] TMA bytes of the raw rows have landed
+  uint64_t* tfull = rawfull + P.nstage;   // [2]  accumulator set ready for its epilogue warpgroup
   uint64_t* tempty = tfull + 2;           // [2]  accumulator set drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.nstage; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < P.nstage; ++i) {
+      mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); mbar_init(smem_u32(rawfull + i), 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -195,27 +252,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
 
   if (warp >= PROD_WARP0) {
     // ===================== producers =====================
+    // chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage; warp p owns stages p, p + nprod, ...
     const int p = warp - PROD_WARP0;
-    const long long total = (p < P.nstage) ? my_tiles * nchunks : 0;
-    uint32_t use = 0;
-    for (long long c = p; c < total; c += P.nstage, ++use) {
-      const long long ti = c / nchunks;
-      const int chunk = (int)(c - ti * nchunks);
-      mbar_wait(smem_u32(empty + p), (use & 1) ^ 1, (uint32_t)P.wait_hint);
-      float* a_hi = stages + (size_t)p * 2 * STAGE_FLOATS;
-      float* a_lo = a_hi + STAGE_FLOATS;
-      const long long row0 = (t_begin + ti) * BM;
-      switch (a.mode) {
-        case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-        case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-        case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-        case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-        case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-        default: produce_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+    const int own = (p < P.nprod) ? (P.nstage - p + P.nprod - 1) / P.nprod : 0;
+    const long long total = my_tiles * nchunks;
+    auto chunk_of = [&](long long i) -> long long { return (i / own) * P.nstage + p + (i % own) * P.nprod; };
+    const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
+    auto issue = [&](long long c) {      // wait for the stage to drain, then start the TMA copy of the raw rows
+      const int stage = (int)(c % P.nstage);
+      const uint32_t use = (uint32_t)(c / P.nstage);
+      mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1, (uint32_t)P.wait_hint);
+      if (lane == 0) {
+        const long long ti = c / nchunks;
+        const int chunk = (int)(c - ti * nchunks);
+        const int r0 = (int)((t_begin + ti) * BM);
+        float* a_hi = stages + (size_t)stage * 2 * STAGE_FLOATS;
+        const uint32_t bar = smem_u32(rawfull + stage);
+        mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
+        tma_load_2d(smem_u32(a_hi), &tmA, chunk * KC, r0, bar);
+        if (has2) tma_load_2d(smem_u32(a_hi + STAGE_FLOATS), &tmA2, chunk * KC, r0, bar);
       }
-      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(full + p));
+    };
+    if (own > 0) {
+      if (P.tma)
+        for (long long i = 0; i < own - 1; ++i) { const long long c = chunk_of(i); if (c < total) issue(c); }
+      for (long long i = 0;; ++i) {
+        const long long c = chunk_of(i);
+        if (c >= total) break;
+        const int stage = (int)(c % P.nstage);
+        const uint32_t use = (uint32_t)(c / P.nstage);
+        const long long ti = c / nchunks;
+        const int chunk = (int)(c - ti * nchunks);
+        float* a_hi = stages + (size_t)stage * 2 * STAGE_FLOATS;
+        float* a_lo = a_hi + STAGE_FLOATS;
+        const long long row0 = (t_begin + ti) * BM;
+        if (P.tma) {
+          const long long cn = chunk_of(i + own - 1);
+          if (cn < total) issue(cn);
+          mbar_wait(smem_u32(rawfull + stage), use & 1, (uint32_t)P.wait_hint);
+          switch (a.mode) {
+            case PRO_NONE: transform_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_RELU: transform_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_GATE_SWISH: transform_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BNBWD: transform_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_ABSDIFF: transform_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            default: transform_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+          }
+        } else {
+          mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1, (uint32_t)P.wait_hint);
+          switch (a.mode) {
+            case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            default: produce_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(full + stage));
+      }
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
@@ -240,7 +338,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t aoff = (uint32_t)ks * 2 * lboA, boff = (uint32_t)(chunk * 4 + ks * 2) * lboB;
             uint64_t dah, dal, dbh, dbl;
-            if (P.lbo_is_k) {
+            if (P.tma) {       // swizzled 64-byte rows: the second K step starts 32 bytes into the row
+              dah = make_desc_sw64(ahi + (uint32_t)ks * 32, 512); dal = make_desc_sw64(alo + (uint32_t)ks * 32, 512);
+              dbh = make_desc(bhi + boff, lboB, sboB); dbl = make_desc(blo + boff, lboB, sboB);
+            } else if (P.lbo_is_k) {
               dah = make_desc(ahi + aoff, lboA, sboA); dal = make_desc(alo + aoff, lboA, sboA);
               dbh = make_desc(bhi + boff, lboB, sboB); dbl = make_desc(blo + boff, lboB, sboB);
             } else {
@@ -260,23 +361,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
     __syncwarp();
   } else {
     // ===================== epilogue: warpgroup `set` (warps 4*set .. 4*set+3) handles tiles ti % 2 == set ===========
-    const int set = warp >> 2, wq = warp & 3;            // wq = TMEM lane quarter this warp may read
+    const int wg = warp >> 2, wq = warp & 3;             // wq = TMEM lane quarter this warp may read
     float* S = epi + (size_t)warp * P.epi_bufs * 32 * EPI_LD;
     float* S2 = S + 32 * EPI_LD;      // only valid when P.epi_bufs == 2
     float* st = s_stat + (size_t)warp * 2 * P.NpA;
     const bool has_stats = g.stats != nullptr;
     const int ncc = (NpB + 31) / 32;
-    const int bar_id = 1 + set;
+    const int bar_id = 1 + wg;
     long long cur_samp = -1;
     auto flush = [&](long long samp) {
       // the four warps of this warpgroup add their partial sums into the global statistics of `samp`
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      const float* wg = s_stat + (size_t)(set * 4) * 2 * P.NpA;
+      const float* wgs = s_stat + (size_t)(wg * 4) * 2 * P.NpA;
       for (int cidx = (threadIdx.x & 127); cidx < NpB; cidx += 128) {
         if (n0 + cidx < g.Ns) {
           float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { t1 += wg[(w * 2 + 0) * P.NpA + cidx]; t2 += wg[(w * 2 + 1) * P.NpA + cidx]; }
+          for (int w = 0; w < 4; ++w) { t1 += wgs[(w * 2 + 0) * P.NpA + cidx]; t2 += wgs[(w * 2 + 1) * P.NpA + cidx]; }
           atomicAdd(g.stats + (samp * 2 + 0) * g.Ns + n0 + cidx, (double)t1);
           atomicAdd(g.stats + (samp * 2 + 1) * g.Ns + n0 + cidx, (double)t2);
         }
@@ -285,7 +386,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
       for (int i = lane; i < 2 * P.NpA; i += 32) st[i] = 0.f;
       __syncwarp();
     };
-    for (long long ti = set; ti < my_tiles; ti += 2) {
+    for (long long ti = wg; ti < my_tiles; ti += NWG) {
+      const int set = (int)(ti & 1);
       const long long row0 = (t_begin + ti) * BM;
       const long long last = row0 + BM - 1 < g.M - 1 ? row0 + BM - 1 : g.M - 1;
       const long long samp0 = row0 / g.rows_per_sample;
@@ -302,8 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
       for (int cc = 0; cc < ncc; ++cc) {
         {
           float r[32], r2[32];
-          tmem_ld32(t_main + (uint32_t)(cc * 32), r);
-          tmem_ld32(t_corr + (uint32_t)(cc * 32), r2);
+          tmem_ld32x2(t_main + (uint32_t)(cc * 32), t_corr + (uint32_t)(cc * 32), r, r2);
           if (cc == ncc - 1) {     // both accumulators fully read by this warp: hand the set back to the MMA issuer
             tc_fence_before();
             __syncwarp();
@@ -421,9 +522,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_gemm_tc_kernel(const Params P)
 
 }  // namespace tc
 
+// Size one kernel variant for this GEMM: N split across grid.y so that the accumulators fit `max_npa` TMEM columns
+// each and the resident weights (both halves) fit in `budget` next to >= `min_stage` pipeline stages.
+template <int NEPI, int NPROD>
+static bool tc_plan(tc::Params& P, size_t budget, int max_npa, int min_stage, int& nsplit, size_t& smem) {
+  const GemmArgs& g = P.g;
+  const int K = g.a.K;
+  const int Np = (g.Ns + 15) / 16 * 16;
+  int NpB = Np;
+  size_t fixed = 0;
+  for (nsplit = 1;; ++nsplit) {
+    NpB = ((Np / 16 + nsplit - 1) / nsplit) * 16;
+    const int NpA = (NpB + 31) / 32 * 32;
+    if (NpA > max_npa) continue;
+    fixed = (size_t)2 * NpB * K * 4 + (size_t)NEPI * P.epi_bufs * 32 * tc::EPI_LD * 4 + (size_t)NEPI * 2 * NpA * 4 + 512;
+    if (fixed + (size_t)min_stage * 2 * tc::STAGE_FLOATS * 4 <= budget) break;
+    if (NpB <= 16) return false;
+  }
+  nsplit = (Np + NpB - 1) / NpB;
+  P.NpB = NpB;
+  P.NpA = (NpB + 31) / 32 * 32;
+  int cols = 32;
+  while (cols < 4 * P.NpA) cols <<= 1;
+  P.tmem_cols = cols;
+  int nstage = (int)((budget - fixed) / ((size_t)2 * tc::STAGE_FLOATS * 4));
+  // gather path: one stage per producer warp; TMA path: spare stages hold copies in flight (up to 3 per warp)
+  const int cap = P.tma ? (3 * NPROD < 16 ? 3 * NPROD : 16) : NPROD;
+  if (nstage > cap) nstage = cap;
+  P.nstage = nstage;
+  P.nprod = nstage < NPROD ? nstage : NPROD;
+  smem = fixed + (size_t)nstage * 2 * tc::STAGE_FLOATS * 4;
+  return true;
+}
+
+template <int NEPI, int NPROD>
+static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensorMap& tmA2, int ctas, int nsplit, size_t smem,
+                     cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<NEPI, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return C3D_ERR_SMEM;
+  const long long ntiles = (P.g.M + tc::BM - 1) / tc::BM;
+  long long gx = ctas / nsplit;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  dim3 grid((unsigned)gx, (unsigned)nsplit);
+  tc::pw_gemm_tc_kernel<NEPI, NPROD><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(P, tmA, tmA2);
+  return c3d_check_last(cudaGetLastError());
+}
+
 // Host-side eligibility + launch.  Returns -1 when the shape / mode is not handled here (caller falls back
-// to the FFMA kernel), otherwise a C3D status.
-int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, int lbo_is_k) {
+// to the FFMA kernel), otherwise a C3D status.  `compact`: 0 = always the 17-warp kernel, 1 = the 9-warp kernel
+// (two CTAs per SM) when it needs no finer N split than the big one, 2 = whenever it fits.  `use_tma`: feed dense
+// operands by TMA (C3D_TC_TMA, default on).
+int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, int lbo_is_k, int compact, int use_tma) {
   const GemmArgs& g = g0;
   if (g.a.map != MAP_DENSE && g.a.map != MAP_SUB2) return -1;
   if (g.epi != EPI_STORE && g.epi != EPI_SWISH_BWD && g.epi != EPI_ADD2) return -1;
@@ -435,41 +585,27 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   P.g = g;
   P.lbo_is_k = lbo_is_k & 1;
   P.wait_hint = lbo_is_k >> 1;      // upper bits of the bring-up flag carry the wait hint (C3D_TC_HINT)
-  const int K = g.a.K;
-  const int Np = (g.Ns + 15) / 16 * 16;
-  // split N across grid.y: <= 128 accumulator columns per CTA (4 TMEM accumulators of <= 128 columns) and the
-  // resident weights (both halves) must fit next to >= 3 pipeline stages
-  const size_t budget = 224 * 1024;
   P.epi_bufs = (g.epi == EPI_SWISH_BWD && g.stats) ? 2 : 1;
-  int nsplit = 1, NpB = Np;
-  size_t fixed = 0;
-  for (;; ++nsplit) {
-    NpB = ((Np / 16 + nsplit - 1) / nsplit) * 16;
-    const int NpA = (NpB + 31) / 32 * 32;
-    if (NpA > 128) continue;
-    fixed = (size_t)2 * NpB * K * 4 + (size_t)tc::NEPI * P.epi_bufs * 32 * tc::EPI_LD * 4 + (size_t)tc::NEPI * 2 * NpA * 4 + 256;
-    if (fixed + (size_t)4 * 2 * tc::STAGE_FLOATS * 4 <= budget) break;
-    if (NpB <= 16) return -1;
-  }
-  nsplit = (Np + NpB - 1) / NpB;
-  P.NpB = NpB;
-  P.NpA = (NpB + 31) / 32 * 32;
-  int cols = 32;
-  while (cols < 4 * P.NpA) cols <<= 1;
-  P.tmem_cols = cols;
-  int nstage = (int)((budget - fixed) / ((size_t)2 * tc::STAGE_FLOATS * 4));
-  if (nstage > tc::NPROD) nstage = tc::NPROD;
-  P.nstage = nstage;
   P.dense_contig = (g.a.map == MAP_DENSE && g.a.img_stride == (long long)g.a.OHW * g.a.ld &&
                     (g.a.A2 == nullptr || g.a.img_stride2 == (long long)g.a.OHW * g.a.ld)) ? 1 : 0;
-  const size_t smem = fixed + (size_t)nstage * 2 * tc::STAGE_FLOATS * 4;
-  cudaError_t e = cudaFuncSetAttribute(tc::pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return C3D_ERR_SMEM;
-  const long long ntiles = (g.M + tc::BM - 1) / tc::BM;
-  long long gx = num_sms / nsplit;
-  if (gx < 1) gx = 1;
-  if (gx > ntiles) gx = ntiles;
-  dim3 grid((unsigned)gx, (unsigned)nsplit);
-  tc::pw_gemm_tc_kernel<<<grid, tc::NTHREADS, smem, stream>>>(P);
-  return c3d_check_last(cudaGetLastError());
+  // TMA feed: rows must be uniformly strided (dense map); the second operand shares the row geometry
+  CUtensorMap tmA, tmA2;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmA2, 0, sizeof(tmA2));
+  P.tma = 0;
+  if (use_tma && P.dense_contig) {
+    const bool has2 = (g.a.mode == PRO_BNBWD || g.a.mode == PRO_ABSDIFF || g.a.mode == PRO_MASK_POS);
+    bool ok = tc::make_tmap_rows(&tmA, g.a.A, g.a.K, g.M, g.a.ld, tc::BM);
+    if (ok && has2) ok = tc::make_tmap_rows(&tmA2, g.a.A2, g.a.K, g.M, g.a.ld, tc::BM);
+    P.tma = ok ? 1 : 0;
+  }
+  tc::Params Pb = P, Pc = P;
+  int ns_b = 0, ns_c = 0;
+  size_t smem_b = 0, smem_c = 0;
+  const bool ok_b = tc_plan<8, 8>(Pb, 224 * 1024, 128, 4, ns_b, smem_b);
+  // two CTAs per SM: half the shared memory (minus the 1 KB the driver reserves per CTA) and half the TMEM columns
+  const bool ok_c = compact > 0 && tc_plan<4, 4>(Pc, 111 * 1024, 64, 3, ns_c, smem_c) && (long long)(g.M + tc::BM - 1) / tc::BM >= 2LL * num_sms;
+  if (ok_c && (compact >= 2 || !ok_b || ns_c <= ns_b)) return tc_launch<4, 4>(Pc, tmA, tmA2, 2 * num_sms, ns_c, smem_c, stream);
+  if (!ok_b) return -1;
+  return tc_launch<8, 8>(Pb, tmA, tmA2, num_sms, ns_b, smem_b, stream);
 }
