@@ -1,0 +1,517 @@
+// Depthwise 3x3x3 Conv3d, stride 1 (X3D conv_b of every non-first block, model/x3d.py:184-193): row-streaming
+// kernels that read every input element from HBM once (plus a one-column halo per 32-column strip).
+//
+// Work unit = (sample, block of 32 channels, strip of 32 image columns); a CTA marches down the rows of a unit.
+// The T frames of strip row r (34 pixels x 32 channels each, halo columns included) land in a ring of shared
+// memory row slots by cp.async (16 bytes = 4 channels per request), D rows ahead of the row being computed.
+// Forward: the thread that requested a piece applies relu(bn_a(.)) to it in place — once per element instead of
+// once per tap — then one __syncthreads per row and every thread computes its outputs from three ring rows.
+//   thread  = (channel, group of 4 adjacent columns), all T frames and the channel's 27 taps in registers;
+//             a warp reads 32 consecutive channels of one pixel: 128-byte rows, conflict-free, and because the
+//             slot geometry is a compile-time constant every shared load is base + immediate
+//   work    = (unit, row) steps, linearised and cut into equal contiguous spans, one span per CTA
+// Zero padding lives in the ring: pieces outside the image are zero-filled by cp.async and skipped by the
+// transform (padding is zero in the ACTIVATED domain).
+#include <stdlib.h>
+
+#include "c3d_common.cuh"
+
+namespace dwr {
+
+constexpr int NT = 256;
+constexpr int CB = 32;                // channels per block
+constexpr int SEGW = 32;              // image columns per strip
+constexpr int PIX = SEGW + 2;         // ring pixels per row (with halo columns)
+constexpr int TS = PIX * CB;          // floats per frame of a ring row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct Geo {
+  int N, IH, IW, C, Cs;
+  int nCB, nSEG;       // channel blocks, column strips
+  int R, D;            // ring slots, rows requested ahead of the computed row (R >= D + 4)
+  long long total_steps, steps_per_cta;
+};
+
+// Per-thread description of the 16-byte pieces it moves for every ring row (the same for all rows of a unit)
+template <int T>
+struct Pieces {
+  static constexpr int E = T * PIX * (CB / 4);
+  static constexpr int NE = (E + NT - 1) / NT;
+  int s_off[NE];       // float offset inside a slot
+  int g_off[NE];       // element offset from (sample, frame 0, row 0, strip column -1, block channel 0)
+  uint32_t ok;         // bit i: piece i exists and lies inside the image / channel range of the current unit
+  uint32_t exists;
+  __device__ __forceinline__ void init(int tid, int IH, int IW, int Cs) {
+    exists = 0;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const int e = tid + i * NT;
+      s_off[i] = 0; g_off[i] = 0;
+      if (e < E) {
+        const int c4 = e & 7, r = e >> 3;
+        const int p = r % PIX, ti = r / PIX;
+        s_off[i] = (ti * PIX + p) * CB + c4 * 4;
+        g_off[i] = (ti * IH * IW + p) * Cs + c4 * 4;
+        exists |= 1u << i;
+      }
+    }
+    ok = 0;
+  }
+  __device__ __forceinline__ void set_unit(int tid, int seg_start, int c0, int IW, int Cs) {
+    ok = 0;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      if (exists >> i & 1) {
+        const int e = tid + i * NT;
+        const int c4 = e & 7, p = (e >> 3) % PIX;
+        const int iw = seg_start - 1 + p;
+        if (iw >= 0 && iw < IW && c0 + c4 * 4 < Cs) ok |= 1u << i;
+      }
+    }
+  }
+};
+
+struct Unit { int n, cb, sg, r0, r1; };     // rows [r0, r1) of (sample, channel block, strip)
+
+__device__ __forceinline__ Unit decode(long long step, long long s1, const Geo& G) {
+  Unit u;
+  const int unit = (int)(step / G.IH);
+  u.r0 = (int)(step - (long long)unit * G.IH);
+  const long long left = s1 - step;
+  u.r1 = (long long)(G.IH - u.r0) < left ? G.IH : u.r0 + (int)left;
+  u.sg = unit % G.nSEG;
+  const int t = unit / G.nSEG;
+  u.cb = t % G.nCB;
+  u.n = t / G.nCB;
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
+                                                            const float* __restrict__ w, float* __restrict__ Y,
+                                                            double* __restrict__ stats, const Geo G) {
+  constexpr int SF = T * TS;                          // floats per ring slot
+  extern __shared__ __align__(16) float sm[];
+  float* ring = sm;                                   // [R][T][PIX][CB]
+  float* s_bn = ring + (size_t)G.R * SF;              // [3][CB] mean, scale, beta of the current channel block
+  double* s_st = reinterpret_cast<double*>(s_bn + 4 * CB);     // [2][CB]
+  const int tid = threadIdx.x;
+  const int cl = tid & 31, grp = tid >> 5;            // channel inside the block, column group (4 columns)
+  const uint32_t ring_u32 = smem_u32(ring);
+  const long long img = (long long)G.IH * G.IW * G.Cs;
+  const long long rowstride = (long long)G.IW * G.Cs;
+
+  Pieces<T> pc;
+  pc.init(tid, G.IH, G.IW, G.Cs);
+
+  const long long s0 = (long long)blockIdx.x * G.steps_per_cta;
+  long long s1 = s0 + G.steps_per_cta;
+  if (s1 > G.total_steps) s1 = G.total_steps;
+
+  long long step = s0;
+  while (step < s1) {
+    const Unit u = decode(step, s1, G);
+    const int c0 = u.cb * CB, seg_start = u.sg * SEGW;
+    const int c = c0 + cl;
+    const bool c_ok = c < G.Cs;
+
+    __syncthreads();                                  // the previous unit's compute and flush are finished
+    if (tid < 3 * CB) {
+      const int k = tid >> 5, cc = tid & 31;
+      const int src = k == 0 ? 0 : k == 1 ? 2 : 3;    // mean, scale, beta rows of the parameter block
+      s_bn[tid] = (c0 + cc < G.Cs) ? __ldg(bnp + src * G.Cs + c0 + cc) : 0.f;
+    }
+    if (tid < 2 * CB) s_st[tid] = 0.0;
+    pc.set_unit(tid, seg_start, c0, G.IW, G.Cs);
+    float wr[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f;
+    // element (sample, frame 0, row 0, strip column -1, block channel 0): only dereferenced where pc.ok says so
+    const float* Xu = X + (long long)u.n * T * img + (long long)(seg_start - 1) * G.Cs + c0;
+    float* Yt = Y + (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 4 * grp) * G.Cs + c;   // frame 0, row r0
+    int nvalid = G.IW - (seg_start + 4 * grp);        // valid columns of this thread's group
+    nvalid = nvalid < 0 ? 0 : nvalid > 4 ? 4 : nvalid;
+    if (!c_ok) nvalid = 0;
+    double st_s = 0.0, st_q = 0.0;
+
+    // ring bookkeeping: slot of row r is (r - r0 + 1) mod R, tracked incrementally
+    int issue_row = u.r0 - 1, issue_slot = 0;
+    auto issue = [&]() {
+      const bool row_ok = issue_row >= 0 && issue_row < G.IH;
+      const uint32_t dst0 = ring_u32 + (uint32_t)(issue_slot * SF) * 4;
+      const float* src0 = Xu + (long long)issue_row * rowstride;
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.exists >> i & 1) {
+          const bool ok = row_ok && (pc.ok >> i & 1);
+          cp_async16(dst0 + (uint32_t)pc.s_off[i] * 4, ok ? (const void*)(src0 + pc.g_off[i]) : (const void*)X, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      ++issue_row;
+      if (++issue_slot == G.R) issue_slot = 0;
+    };
+    auto transform = [&](int row, int slot) {         // relu(bn_a(.)) in place on this thread's own pieces
+      if (row < 0 || row >= G.IH) return;
+      float* base = ring + (size_t)slot * SF;
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.ok >> i & 1) {
+          const int c4 = ((tid + i * NT) & 7) * 4;
+          float4* p = reinterpret_cast<float4*>(base + pc.s_off[i]);
+          const float4 mean = *reinterpret_cast<const float4*>(s_bn + c4);
+          const float4 scale = *reinterpret_cast<const float4*>(s_bn + CB + c4);
+          const float4 beta = *reinterpret_cast<const float4*>(s_bn + 2 * CB + c4);
+          *p = f4relu(f4bn(*p, mean, scale, beta));
+        }
+      }
+    };
+
+    // prologue: rows r0-1 .. r0+D requested (slots 0 .. D+1), the first two transformed
+    for (int i = 0; i < G.D + 2; ++i) issue();
+    __syncthreads();                                  // s_bn is visible
+    if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+    transform(u.r0 - 1, 0);
+    transform(u.r0, 1);
+    int sl = 0;                                       // slot of row oh - 1
+    for (int oh = u.r0; oh < u.r1; ++oh) {
+      issue();
+      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
+      const int sl2 = sl1 + 1 >= G.R ? sl1 + 1 - G.R : sl1 + 1;
+      transform(oh + 1, sl2);
+      __syncthreads();
+      if (nvalid > 0) {
+        const int toff = (4 * grp) * CB + cl;
+        const float* b0 = ring + sl * SF + toff;
+        const float* b1 = ring + sl1 * SF + toff;
+        const float* b2 = ring + sl2 * SF + toff;
+        float acc[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[t][q] = 0.f;
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* rp = (kh == 0 ? b0 : kh == 1 ? b1 : b2) + ti * TS;
+            float in[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) in[j] = rp[j * CB];
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int to = ti - kt + 1;
+              if (to < 0 || to >= T) continue;
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const float wv = wr[kt * 9 + kh * 3 + kw];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[to][q] = fmaf(wv, in[q + kw], acc[to][q]);
+              }
+            }
+          }
+        }
+        float sf = 0.f, qf = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          float* yp = Yt + (long long)t * img;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nvalid) {
+              yp[q * G.Cs] = acc[t][q];
+              sf += acc[t][q];
+              qf = fmaf(acc[t][q], acc[t][q], qf);
+            }
+          }
+        }
+        st_s += (double)sf;
+        st_q += (double)qf;
+      }
+      Yt += rowstride;
+      sl = sl1;
+    }
+    cp_async_wait<0>();
+    if (stats) {      // per-sample statistics of this unit: fold the 8 column groups in shared memory, then one atomic each
+      if (nvalid > 0) { atomicAdd(&s_st[cl], st_s); atomicAdd(&s_st[CB + cl], st_q); }
+      __syncthreads();
+      if (tid < 2 * CB) {
+        const int k = tid >> 5, cc = tid & 31;
+        if (c0 + cc < G.Cs) atomicAdd(stats + ((long long)u.n * 2 + k) * G.Cs + c0 + cc, s_st[tid]);
+      }
+    }
+    step += u.r1 - u.r0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: dr = conv_transpose(dy, w) * (a > 0), dW[tap] += sum a * dy, stats_a += (sum dr, sum dr * yhat_a)
+//   dy  (N,T,H,W,Cs)  gradient w.r.t. the raw conv_b output (BN_b / SE / Swish backward already applied)
+//   y_a (N,T,H,W,Cs)  raw conv_a output; a = relu(bn_a(y_a)) is recomputed per thread for its own pixels
+// The ring holds dy rows ih-1 .. ih+1 (input row ih receives taps from output rows ih+1-kh); y_a is only needed at
+// the thread's own pixels and is read straight from global memory while the row's ring data is awaited.  The 27
+// weight-gradient accumulators of the thread's channel stay in registers for a whole unit.
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restrict__ DY, const float* __restrict__ YA,
+                                                            const float* __restrict__ bnp_a, const float* __restrict__ w,
+                                                            float* __restrict__ DR, float* __restrict__ dW,
+                                                            double* __restrict__ stats_a, const Geo G) {
+  constexpr int SF = T * TS;
+  extern __shared__ __align__(16) float sm[];
+  float* ring = sm;                                                  // [R][T][PIX][CB]
+  float* s_dw = ring + (size_t)G.R * SF;                             // [27][CB]
+  double* s_st = reinterpret_cast<double*>(s_dw + 28 * CB);          // [2][CB]
+  const int tid = threadIdx.x;
+  const int cl = tid & 31, grp = tid >> 5;
+  const uint32_t ring_u32 = smem_u32(ring);
+  const long long img = (long long)G.IH * G.IW * G.Cs;
+  const long long rowstride = (long long)G.IW * G.Cs;
+
+  Pieces<T> pc;
+  pc.init(tid, G.IH, G.IW, G.Cs);
+
+  const long long s0 = (long long)blockIdx.x * G.steps_per_cta;
+  long long s1 = s0 + G.steps_per_cta;
+  if (s1 > G.total_steps) s1 = G.total_steps;
+
+  long long step = s0;
+  while (step < s1) {
+    const Unit u = decode(step, s1, G);
+    const int c0 = u.cb * CB, seg_start = u.sg * SEGW;
+    const int c = c0 + cl;
+    const bool c_ok = c < G.Cs;
+
+    __syncthreads();
+    for (int i = tid; i < 27 * CB; i += NT) s_dw[i] = 0.f;
+    if (tid < 2 * CB) s_st[tid] = 0.0;
+    pc.set_unit(tid, seg_start, c0, G.IW, G.Cs);
+    float wr[27], dwacc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) { wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f; dwacc[t] = 0.f; }
+    float mean_a = 0.f, rstd_a = 0.f, scale_a = 0.f, beta_a = 0.f;
+    if (c_ok) {
+      mean_a = __ldg(bnp_a + c); rstd_a = __ldg(bnp_a + G.Cs + c);
+      scale_a = __ldg(bnp_a + 2 * G.Cs + c); beta_a = __ldg(bnp_a + 3 * G.Cs + c);
+    }
+    const float* DYu = DY + (long long)u.n * T * img + (long long)(seg_start - 1) * G.Cs + c0;
+    const long long toff_g = (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 4 * grp) * G.Cs + c;
+    const float* YAt = YA + toff_g;                   // frame 0, row r0, this thread's first column
+    float* DRt = DR + toff_g;
+    int nvalid = G.IW - (seg_start + 4 * grp);
+    nvalid = nvalid < 0 ? 0 : nvalid > 4 ? 4 : nvalid;
+    if (!c_ok) nvalid = 0;
+    double st_s = 0.0, st_t = 0.0;
+
+    int issue_row = u.r0 - 1, issue_slot = 0;
+    auto issue = [&]() {
+      const bool row_ok = issue_row >= 0 && issue_row < G.IH;
+      const uint32_t dst0 = ring_u32 + (uint32_t)(issue_slot * SF) * 4;
+      const float* src0 = DYu + (long long)issue_row * rowstride;
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.exists >> i & 1) {
+          const bool ok = row_ok && (pc.ok >> i & 1);
+          cp_async16(dst0 + (uint32_t)pc.s_off[i] * 4, ok ? (const void*)(src0 + pc.g_off[i]) : (const void*)DY, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      ++issue_row;
+      if (++issue_slot == G.R) issue_slot = 0;
+    };
+
+    for (int i = 0; i < G.D + 2; ++i) issue();
+    int sl = 0;                                       // slot of row ih - 1
+    for (int ih = u.r0; ih < u.r1; ++ih) {
+      issue();
+      // this thread's own y_a values: in flight while the ring row is awaited
+      float ya[T][4];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ya[t][q] = (q < nvalid) ? __ldg(YAt + (long long)t * img + q * G.Cs) : 0.f;
+      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
+      const int sl2 = sl1 + 1 >= G.R ? sl1 + 1 - G.R : sl1 + 1;
+      __syncthreads();
+      if (nvalid > 0) {
+        const int toff = (4 * grp) * CB + cl;
+        const float* b0 = ring + sl2 * SF + toff;      // kh = 0: output row ih + 1
+        const float* b1 = ring + sl1 * SF + toff;      // kh = 1: output row ih
+        const float* b2 = ring + sl * SF + toff;       // kh = 2: output row ih - 1
+        float a[T][4], da[T][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a[t][q] = (q < nvalid) ? fmaxf(fmaf(ya[t][q] - mean_a, scale_a, beta_a), 0.f) : 0.f;
+            da[t][q] = 0.f;
+          }
+#pragma unroll
+        for (int to = 0; to < T; ++to) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* rp = (kh == 0 ? b0 : kh == 1 ? b1 : b2) + to * TS;
+            float dyw[6];                              // output columns (first column of the group) - 1 .. + 4
+#pragma unroll
+            for (int j = 0; j < 6; ++j) dyw[j] = rp[j * CB];
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int ti = to + kt - 1;
+              if (ti < 0 || ti >= T) continue;
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const int tap = kt * 9 + kh * 3 + kw;
+                const float wv = wr[tap];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float d = dyw[q + 2 - kw];     // ow = iw + 1 - kw
+                  da[ti][q] = fmaf(wv, d, da[ti][q]);
+                  dwacc[tap] = fmaf(a[ti][q], d, dwacc[tap]);
+                }
+              }
+            }
+          }
+        }
+        float sf = 0.f, tf = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          float* dp = DRt + (long long)t * img;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q < nvalid) {
+              const float v = a[t][q] > 0.f ? da[t][q] : 0.f;
+              dp[q * G.Cs] = v;
+              sf += v;
+              tf = fmaf(v, (ya[t][q] - mean_a) * rstd_a, tf);
+            }
+          }
+        }
+        st_s += (double)sf;
+        st_t += (double)tf;
+      }
+      YAt += rowstride;
+      DRt += rowstride;
+      sl = sl1;
+    }
+    cp_async_wait<0>();
+    // ---- unit flush: weight gradient and BN_a backward statistics of this channel block ----
+    if (nvalid > 0) {
+#pragma unroll
+      for (int t = 0; t < 27; ++t) atomicAdd(&s_dw[t * CB + cl], dwacc[t]);
+      atomicAdd(&s_st[cl], st_s);
+      atomicAdd(&s_st[CB + cl], st_t);
+    }
+    __syncthreads();
+    for (int i = tid; i < 27 * CB; i += NT) {
+      const int t = i >> 5, cc = i & 31;
+      if (c0 + cc < G.C) atomicAdd(dW + (c0 + cc) * 27 + t, s_dw[i]);
+    }
+    if (tid < 2 * CB) {
+      const int k = tid >> 5, cc = tid & 31;
+      if (c0 + cc < G.Cs) atomicAdd(stats_a + (long long)k * G.Cs + c0 + cc, s_st[tid]);
+    }
+    step += u.r1 - u.r0;
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static bool plan(Geo& G, int T, int N, int IH, int IW, int C, int Cs, size_t extra_smem, size_t& smem, int& grid, int ctas_per_sm) {
+  if (IW < 1 || (Cs & 3) || T < 3 || T > 5) return false;
+  if ((long long)T * IH * IW * Cs >= (1LL << 31)) return false;        // per-sample offsets are 32-bit
+  G.N = N; G.IH = IH; G.IW = IW; G.C = C; G.Cs = Cs;
+  G.nCB = (Cs + CB - 1) / CB;
+  G.nSEG = (IW + SEGW - 1) / SEGW;
+  const size_t slot = (size_t)T * TS * 4;
+  int dev = 0, sms = 148, max_smem = 227 * 1024;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t budget = (size_t)(max_smem + 1024) / ctas_per_sm - 1024;
+  G.D = 2; G.R = 6;
+  if (G.R * slot + extra_smem > budget) { G.D = 1; G.R = 5; }
+  if (G.R * slot + extra_smem > budget) return false;
+  smem = G.R * slot + extra_smem;
+  G.total_steps = (long long)N * G.nCB * G.nSEG * IH;
+  long long g = (long long)sms * ctas_per_sm;
+  if (g > G.total_steps) g = G.total_steps;
+  G.steps_per_cta = (G.total_steps + g - 1) / g;
+  grid = (int)((G.total_steps + G.steps_per_cta - 1) / G.steps_per_cta);
+  return true;
+}
+
+}  // namespace dwr
+
+// Returns -1 when the shape is not handled here (caller uses the generic kernel), else a C3D status.
+int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, float* Y, double* stats, int N, int T, int IH,
+                           int IW, int C, int Cs, cudaStream_t st) {
+  if (!dwr::env_int("C3D_DW_RING", 1)) return -1;
+  dwr::Geo G;
+  size_t smem = 0;
+  int grid = 0;
+  const size_t extra = (size_t)(4 * dwr::CB * 4 + 2 * dwr::CB * 8);        // s_bn [4][CB] floats + s_st [2][CB] doubles
+  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1)) return -1;
+  cudaError_t e;
+  switch (T) {
+    case 3:
+      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_fwd_ring_kernel<3><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      break;
+    case 4:
+      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_fwd_ring_kernel<4><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      break;
+    default:
+      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_fwd_ring_kernel<5><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      break;
+  }
+  return c3d_check_last(cudaGetLastError());
+}
+
+// dy = du already transformed by the elementwise pre-pass (dw_dy_kernel).  Returns -1 when not handled here.
+int c3d_launch_dw_bwd_ring(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW,
+                           double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st) {
+  if (!dwr::env_int("C3D_DW_RING", 1)) return -1;
+  dwr::Geo G;
+  size_t smem = 0;
+  int grid = 0;
+  const size_t extra = (size_t)(28 * dwr::CB * 4 + 2 * dwr::CB * 8);       // s_dw [27][CB] floats (+ pad) + s_st [2][CB] doubles
+  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1)) return -1;
+  cudaError_t e;
+  switch (T) {
+    case 3:
+      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_bwd_ring_kernel<3><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
+      break;
+    case 4:
+      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_bwd_ring_kernel<4><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
+      break;
+    default:
+      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return C3D_ERR_SMEM;
+      dwr::dw_bwd_ring_kernel<5><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
+      break;
+  }
+  return c3d_check_last(cudaGetLastError());
+}

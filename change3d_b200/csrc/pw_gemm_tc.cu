@@ -17,6 +17,9 @@
 // Each tile owns two TMEM accumulators: the main term Ah*Bh and the correction terms Al*Bh + Ah*Bl are
 // accumulated separately and added in the epilogue — the tensor core's fp32 accumulation rounds toward
 // zero, and keeping the 2^-11-sized terms out of the main chain cuts that bias ~3x.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "pw_gemm.cuh"
 
 #include "tc_common.cuh"
@@ -45,6 +48,8 @@ struct Params {
   int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
   int wait_hint;     // mbarrier try_wait suspend hint in ns (0 = none)
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
+  uint32_t rps;      // rows per batch sample, clamped to 2^31 - 1 (M < 2^31: all row arithmetic fits 32 bits)
+  unsigned long long* dbg;   // C3D_TC_DBG=1: per-warp wait/work cycle counters of one CTA ([32 warps][8]), else null
 };
 
 // One producer warp fills one stage: 128 rows x 16 channels, lane = (row % 8, 16-byte chunk), 16 row groups.
@@ -160,22 +165,30 @@ __device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& 
   const long long left = P.g.M - row0;
   const int nvalid = left < BM ? (int)left : BM;
   const int po = rl * 16 + ((qq ^ ((rl >> 1) & 3)) << 2);
-#pragma unroll 4
-  for (int b = 0; b < 16; ++b) {
-    const int r = b * 8 + rl;
-    float4* ph = reinterpret_cast<float4*>(a_hi + b * 128 + po);
-    float4* pl = reinterpret_cast<float4*>(a_lo + b * 128 + po);
-    const float4 v = *ph;
-    const float4 v2 = HAS2 ? *pl : f4zero();
-    float4 g4 = (r >= gsplit) ? g1 : g0;
-    if (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast && r < nvalid)
-      g4 = ldg4(s.gate + (long long)(((uint32_t)(row0 + r) / (uint32_t)s.OHW) / (uint32_t)s.frames_per_sample) * s.ld + k);
-    float4 x = prologue<MODE>(cp, v, v2, g4);
-    if (r >= nvalid) x = f4zero();     // TMA zero-fills rows past M; keep them zero through the prologue
-    float4 hi, lo;
-    split4(x, hi, lo);
-    *ph = hi;
-    *pl = lo;
+  const bool slow_gate = (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast);
+  // batches of 4 row groups: all shared-memory loads of a batch are issued before its first store (the in-place
+  // stores would otherwise order every load behind the previous iteration's stores)
+#pragma unroll
+  for (int b0 = 0; b0 < 16; b0 += 4) {
+    float4 v[4], v2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(a_hi + (b0 + i) * 128 + po);
+      v2[i] = HAS2 ? *reinterpret_cast<const float4*>(a_lo + (b0 + i) * 128 + po) : f4zero();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (b0 + i) * 8 + rl;
+      float4 g4 = (r >= gsplit) ? g1 : g0;
+      if (slow_gate && r < nvalid)
+        g4 = ldg4(s.gate + (long long)(((uint32_t)(row0 + r) / (uint32_t)s.OHW) / (uint32_t)s.frames_per_sample) * s.ld + k);
+      float4 x = prologue<MODE>(cp, v[i], v2[i], g4);
+      if (r >= nvalid) x = f4zero();     // TMA zero-fills rows past M; keep them zero through the prologue
+      float4 hi, lo;
+      split4(x, hi, lo);
+      *reinterpret_cast<float4*>(a_hi + (b0 + i) * 128 + po) = hi;
+      *reinterpret_cast<float4*>(a_lo + (b0 + i) * 128 + po) = lo;
+    }
   }
 }
 
@@ -188,7 +201,13 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const GemmArgs& g = P.g;
   TileSrc a = g.a;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (stage cursors, descriptors, barrier addresses) in uniform registers — tcgen05.mma / TMA take uniform operands,
+  // and values of unknown uniformity cost a R2UR waterfall loop around every single instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0;
+  long long d_t0 = dbg_on ? clock64() : 0, d_a = 0, d_b = 0, d_c = 0, d_n = 0;
+#define DBG_T(acc, stmt) do { if (dbg_on) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
   const int n0 = blockIdx.y * P.NpB;
   const int K = a.K;                      // multiple of 8
   const int NpB = P.NpB;
@@ -242,123 +261,143 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const long long d_t1 = dbg_on ? clock64() : 0;
 
   const long long ntiles = (g.M + BM - 1) / BM;
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
   const long long t_begin = (long long)blockIdx.x * tpc;
   const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
-  const long long my_tiles = t_end > t_begin ? t_end - t_begin : 0;
+  const int my_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const uint32_t stages_u32 = smem_u32(stages);
+  constexpr uint32_t STAGE_BYTES = 2 * STAGE_FLOATS * 4;     // hi + lo
 
   if (warp >= PROD_WARP0) {
     // ===================== producers =====================
-    // chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage; warp p owns stages p, p + nprod, ...
+    // Chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage.  nstage is a multiple of nprod, so warp p
+    // handles chunks p, p + nprod, ... and cycles through its own stages p, p + nprod, ...; (tile, chunk, stage, phase)
+    // advance incrementally — no divisions in the loop.
     const int p = warp - PROD_WARP0;
-    const int own = (p < P.nprod) ? (P.nstage - p + P.nprod - 1) / P.nprod : 0;
-    const long long total = my_tiles * nchunks;
-    auto chunk_of = [&](long long i) -> long long { return (i / own) * P.nstage + p + (i % own) * P.nprod; };
-    const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
-    auto issue = [&](long long c) {      // wait for the stage to drain, then start the TMA copy of the raw rows
-      const int stage = (int)(c % P.nstage);
-      const uint32_t use = (uint32_t)(c / P.nstage);
-      mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1, (uint32_t)P.wait_hint);
-      if (lane == 0) {
-        const long long ti = c / nchunks;
-        const int chunk = (int)(c - ti * nchunks);
-        const int r0 = (int)((t_begin + ti) * BM);
-        float* a_hi = stages + (size_t)stage * 2 * STAGE_FLOATS;
-        const uint32_t bar = smem_u32(rawfull + stage);
-        mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
-        tma_load_2d(smem_u32(a_hi), &tmA, chunk * KC, r0, bar);
-        if (has2) tma_load_2d(smem_u32(a_hi + STAGE_FLOATS), &tmA2, chunk * KC, r0, bar);
-      }
-      __syncwarp();
-    };
-    if (own > 0) {
+    if (p < P.nprod && my_tiles > 0) {
+      const int own = P.nstage / P.nprod;
+      const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
+      struct Cursor { int ti, chunk, stage; uint32_t phase; };
+      auto advance = [&](Cursor& c) {
+        c.chunk += P.nprod;
+        while (c.chunk >= nchunks) { c.chunk -= nchunks; ++c.ti; }
+        c.stage += P.nprod;
+        if (c.stage >= P.nstage) { c.stage -= P.nstage; c.phase ^= 1u; }
+      };
+      auto issue = [&](const Cursor& c) {      // wait for the stage to drain, then start the TMA copy of the raw rows
+        DBG_T(d_a, mbar_wait(smem_u32(empty + c.stage), c.phase ^ 1u, (uint32_t)P.wait_hint));
+        if (lane == 0) {
+          const int r0 = (int)((t_begin + c.ti) * BM);
+          const uint32_t dst = stages_u32 + (uint32_t)c.stage * STAGE_BYTES;
+          const uint32_t bar = smem_u32(rawfull + c.stage);
+          mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
+          tma_load_2d(dst, &tmA, c.chunk * KC, r0, bar);
+          if (has2) tma_load_2d(dst + STAGE_FLOATS * 4, &tmA2, c.chunk * KC, r0, bar);
+        }
+        __syncwarp();
+      };
+      Cursor cur, nxt;
+      cur.ti = 0; cur.chunk = p; cur.stage = p; cur.phase = 0;
+      while (cur.chunk >= nchunks) { cur.chunk -= nchunks; ++cur.ti; }
+      nxt = cur;
       if (P.tma)
-        for (long long i = 0; i < own - 1; ++i) { const long long c = chunk_of(i); if (c < total) issue(c); }
-      for (long long i = 0;; ++i) {
-        const long long c = chunk_of(i);
-        if (c >= total) break;
-        const int stage = (int)(c % P.nstage);
-        const uint32_t use = (uint32_t)(c / P.nstage);
-        const long long ti = c / nchunks;
-        const int chunk = (int)(c - ti * nchunks);
-        float* a_hi = stages + (size_t)stage * 2 * STAGE_FLOATS;
+        for (int i = 0; i < own - 1; ++i) { if (nxt.ti < my_tiles) issue(nxt); advance(nxt); }
+      while (cur.ti < my_tiles) {
+        float* a_hi = stages + (size_t)cur.stage * 2 * STAGE_FLOATS;
         float* a_lo = a_hi + STAGE_FLOATS;
-        const long long row0 = (t_begin + ti) * BM;
+        const long long row0 = (t_begin + cur.ti) * BM;
         if (P.tma) {
-          const long long cn = chunk_of(i + own - 1);
-          if (cn < total) issue(cn);
-          mbar_wait(smem_u32(rawfull + stage), use & 1, (uint32_t)P.wait_hint);
+          if (nxt.ti < my_tiles) issue(nxt);
+          advance(nxt);
+          DBG_T(d_b, mbar_wait(smem_u32(rawfull + cur.stage), cur.phase, (uint32_t)P.wait_hint));
+          ++d_n;
+          const long long t_x = dbg_on ? clock64() : 0;
           switch (a.mode) {
-            case PRO_NONE: transform_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_RELU: transform_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_GATE_SWISH: transform_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BNBWD: transform_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_ABSDIFF: transform_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            default: transform_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_NONE: transform_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_RELU: transform_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_GATE_SWISH: transform_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BNBWD: transform_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_ABSDIFF: transform_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            default: transform_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
           }
+          if (dbg_on) d_c += clock64() - t_x;
         } else {
-          mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1, (uint32_t)P.wait_hint);
+          DBG_T(d_a, mbar_wait(smem_u32(empty + cur.stage), cur.phase ^ 1u, (uint32_t)P.wait_hint));
+          ++d_n;
+          const long long t_x = dbg_on ? clock64() : 0;
           switch (a.mode) {
-            case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, chunk, a_hi, a_lo, lane); break;
-            default: produce_chunk<PRO_MASK_POS>(P, a, row0, chunk, a_hi, a_lo, lane); break;
+            case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            default: produce_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
           }
+          if (dbg_on) d_c += clock64() - t_x;
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(full + stage));
+        if (lane == 0) mbar_arrive(smem_u32(full + cur.stage));
+        advance(cur);
       }
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow, uniform operands); lane 0 alone issues the MMAs and
+    // commits.  Everything that does not change per chunk is hoisted (descriptor templates, barrier addresses) and
+    // the stage / phase counters advance incrementally: this instruction stream is the pipeline's pacemaker.
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NpB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lboA = 16 * 128, sboA = 128;                       // stage layout [k-chunk][row group][8][16 B]
       const uint32_t lboB = (uint32_t)(NpB >> 3) * 128, sboB = 128;     // weights     [k-chunk][col group][8][16 B]
-      const uint32_t bhi = smem_u32(B_hi), blo = smem_u32(B_lo);
-      long long c = 0;
-      for (long long ti = 0; ti < my_tiles; ++ti) {
-        const int set = (int)(ti & 1);
-        mbar_wait(smem_u32(tempty + set), ((uint32_t)(ti >> 1) & 1) ^ 1, (uint32_t)P.wait_hint);
+      // descriptor templates with a zero start address; the address field (bits 0-13, 16-byte units) is added per use
+      uint64_t tA, tB;
+      uint32_t a_kstep;                                                  // byte offset of the second K step inside a stage half
+      if (P.tma) { tA = make_desc_sw64(0, 512); a_kstep = 32; }
+      else if (P.lbo_is_k) { tA = make_desc(0, lboA, sboA); a_kstep = 2 * lboA; }
+      else { tA = make_desc(0, sboA, lboA); a_kstep = 2 * lboA; }
+      tB = (P.tma || P.lbo_is_k) ? make_desc(0, lboB, sboB) : make_desc(0, sboB, lboB);
+      const uint64_t dB_hi0 = tB + (uint64_t)(smem_u32(B_hi) >> 4), dB_lo0 = tB + (uint64_t)(smem_u32(B_lo) >> 4);
+      const uint32_t b_kstep16 = (2 * lboB) >> 4;                       // descriptor units per K step of 8
+      const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int set = ti & 1;
+        DBG_T(d_a, mbar_wait(smem_u32(tempty + set), ((uint32_t)(ti >> 1) & 1) ^ 1, (uint32_t)P.wait_hint));
+        ++d_n;
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * P.NpA);
         const uint32_t d_corr = d_main + (uint32_t)P.NpA;
-        for (int chunk = 0; chunk < nchunks; ++chunk, ++c) {
-          const int stage = (int)(c % P.nstage);
-          mbar_wait(smem_u32(full + stage), (uint32_t)(c / P.nstage) & 1, (uint32_t)P.wait_hint);
+        uint64_t dbh = dB_hi0, dbl = dB_lo0;
+        int kleft = K;
+        uint32_t accum = 0;
+        for (int chunk = 0; chunk < nchunks; ++chunk, kleft -= KC) {
+          DBG_T(d_b, mbar_wait(full0 + (uint32_t)stage * 8, phase, (uint32_t)P.wait_hint));
           tc_fence_after();
-          const uint32_t ahi = smem_u32(stages + (size_t)stage * 2 * STAGE_FLOATS), alo = ahi + STAGE_FLOATS * 4;
-          const int ksteps = (K - chunk * KC) >= KC ? 2 : 1;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t aoff = (uint32_t)ks * 2 * lboA, boff = (uint32_t)(chunk * 4 + ks * 2) * lboB;
-            uint64_t dah, dal, dbh, dbl;
-            if (P.tma) {       // swizzled 64-byte rows: the second K step starts 32 bytes into the row
-              dah = make_desc_sw64(ahi + (uint32_t)ks * 32, 512); dal = make_desc_sw64(alo + (uint32_t)ks * 32, 512);
-              dbh = make_desc(bhi + boff, lboB, sboB); dbl = make_desc(blo + boff, lboB, sboB);
-            } else if (P.lbo_is_k) {
-              dah = make_desc(ahi + aoff, lboA, sboA); dal = make_desc(alo + aoff, lboA, sboA);
-              dbh = make_desc(bhi + boff, lboB, sboB); dbl = make_desc(blo + boff, lboB, sboB);
-            } else {
-              dah = make_desc(ahi + aoff, sboA, lboA); dal = make_desc(alo + aoff, sboA, lboA);
-              dbh = make_desc(bhi + boff, sboB, lboB); dbl = make_desc(blo + boff, sboB, lboB);
-            }
-            const uint32_t first = (chunk == 0 && ks == 0) ? 0u : 1u;
-            umma_tf32(d_main, dah, dbh, idesc, first);
-            umma_tf32(d_corr, dal, dbh, idesc, first);
-            umma_tf32(d_corr, dah, dbl, idesc, 1u);
-          }
-          umma_commit(smem_u32(empty + stage));
+          const uint32_t ahi = stages_u32 + (uint32_t)stage * STAGE_BYTES;
+          const uint64_t dah = tA + (uint64_t)(ahi >> 4), dal = dah + (uint64_t)((STAGE_FLOATS * 4) >> 4);
+          const uint32_t two = (leader && kleft >= KC) ? 1u : 0u;
+          const uint64_t dah2 = dah + (a_kstep >> 4), dal2 = dal + (a_kstep >> 4), dbh2 = dbh + b_kstep16, dbl2 = dbl + b_kstep16;
+          umma_tf32_if(leader, d_main, dah, dbh, idesc, accum);
+          umma_tf32_if(leader, d_corr, dal, dbh, idesc, accum);
+          umma_tf32_if(leader, d_corr, dah, dbl, idesc, 1u);
+          umma_tf32_if(two, d_main, dah2, dbh2, idesc, 1u);
+          umma_tf32_if(two, d_corr, dal2, dbh2, idesc, 1u);
+          umma_tf32_if(two, d_corr, dah2, dbl2, idesc, 1u);
+          umma_commit_if(leader, empty0 + (uint32_t)stage * 8);
+          accum = 1u;
+          dbh += 2 * b_kstep16; dbl += 2 * b_kstep16;
+          if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(tfull + set));
+        umma_commit_if(leader, smem_u32(tfull + set));
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: warpgroup `set` (warps 4*set .. 4*set+3) handles tiles ti % 2 == set ===========
     const int wg = warp >> 2, wq = warp & 3;             // wq = TMEM lane quarter this warp may read
@@ -390,14 +429,27 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
       const int set = (int)(ti & 1);
       const long long row0 = (t_begin + ti) * BM;
       const long long last = row0 + BM - 1 < g.M - 1 ? row0 + BM - 1 : g.M - 1;
-      const long long samp0 = row0 / g.rows_per_sample;
-      const bool straddle = (last / g.rows_per_sample) != samp0;
+      // 32-bit divisions only: a 64-bit division compiles to a subroutine call, after which ptxas no longer keeps the
+      // MMA warp's operands in uniform registers (every tcgen05.mma then sits in a R2UR waterfall loop)
+      const long long samp0 = (long long)((uint32_t)row0 / P.rps);
+      const bool straddle = (long long)((uint32_t)last / P.rps) != samp0;
       const bool full_tile = (row0 + BM <= g.M);
+      // sample of this warp's first row and the first of its 32 rows that belongs to the next sample (>= 32: none)
+      const long long wrow0 = row0 + wq * 32;
+      const bool sp_fast = P.rps >= 32u;
+      long long wsp0 = samp0;
+      int wsplit = 32;
+      if (g.epi == EPI_SWISH_BWD && sp_fast) {
+        if (straddle) wsp0 = (long long)((uint32_t)wrow0 / P.rps);
+        const long long nb = (wsp0 + 1) * (long long)P.rps - wrow0;
+        wsplit = nb < 32 ? (int)nb : 32;
+      }
       if (has_stats && samp0 != cur_samp) {
         if (cur_samp >= 0) flush(cur_samp);
         cur_samp = samp0;
       }
-      mbar_wait(smem_u32(tfull + set), (uint32_t)(ti >> 1) & 1, (uint32_t)P.wait_hint);
+      DBG_T(d_a, mbar_wait(smem_u32(tfull + set), (uint32_t)(ti >> 1) & 1, (uint32_t)P.wait_hint));
+      ++d_n;
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * 2 * P.NpA);
       const uint32_t t_corr = t_main + (uint32_t)P.NpA;
@@ -421,7 +473,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
         const int cl = cc * 32 + 4 * q;          // column inside this CTA's accumulator
         const int col = n0 + cl;
         const bool col_ok = col < g.Ns && cl < NpB;
-        const long long tile_o = (row0 + wq * 32 + (lane >> 3)) * (long long)g.Ns + col;
+        const long long tile_o = (wrow0 + (lane >> 3)) * (long long)g.Ns + col;
         if (g.epi == EPI_STORE) {
           if (col_ok) {
 #pragma unroll
@@ -441,23 +493,39 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
           }
         } else {
           float4 mean = f4zero(), rstd = f4zero(), scale = f4zero(), beta = f4zero();
+          float4 gt0 = make_float4(1.f, 1.f, 1.f, 1.f), gt1 = gt0;
           if (g.epi == EPI_SWISH_BWD && col_ok) {
             mean = ldg4(BNP_MEAN(g.ebnp, g.Ns) + col); rstd = ldg4(BNP_RSTD(g.ebnp, g.Ns) + col);
             scale = ldg4(BNP_SCALE(g.ebnp, g.Ns) + col); beta = ldg4(BNP_BETA(g.ebnp, g.Ns) + col);
+            if (g.egate && sp_fast) {
+              gt0 = ldg4(g.egate + wsp0 * g.Ns + col);
+              if (wsplit < 32 && wrow0 + wsplit < g.M) gt1 = ldg4(g.egate + (wsp0 + 1) * g.Ns + col);
+            }
           }
-#pragma unroll 2
+          // all global reads of the 8 row quads first (memory-level parallelism), then the arithmetic
+          float4 e1[8];
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
-            const long long row = row0 + wq * 32 + rr;
+            e1[i] = f4zero();
+            if (g.E1 && col_ok && wrow0 + rr < g.M) e1[i] = ldg4(g.E1 + tile_o + (long long)(4 * i) * g.Ns);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const long long row = wrow0 + rr;
             float4 v = *reinterpret_cast<const float4*>(S + rr * EPI_LD + 4 * q);
             float4 v2 = f4zero();
             if (row < g.M && col_ok) {
               const long long o = tile_o + (long long)(4 * i) * g.Ns;
               if (g.epi == EPI_SWISH_BWD) {
-                const float4 yb = ldg4(g.E1 + o);
-                const long long sp = row / g.rows_per_sample;
-                float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (g.egate) gt = ldg4(g.egate + sp * g.Ns + col);
+                const float4 yb = e1[i];
+                long long sp = rr >= wsplit ? wsp0 + 1 : wsp0;
+                float4 gt = rr >= wsplit ? gt1 : gt0;
+                if (!sp_fast) {
+                  sp = (long long)((uint32_t)row / P.rps);
+                  if (g.egate) gt = ldg4(g.egate + sp * g.Ns + col);
+                }
                 float yv[4] = {yb.x, yb.y, yb.z, yb.w}, mv[4] = {mean.x, mean.y, mean.z, mean.w};
                 float rv[4] = {rstd.x, rstd.y, rstd.z, rstd.w}, sv[4] = {scale.x, scale.y, scale.z, scale.w};
                 float bv[4] = {beta.x, beta.y, beta.z, beta.w}, gv[4] = {gt.x, gt.y, gt.z, gt.w};
@@ -478,7 +546,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
                 v2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
                 st4(g.Y + o, v);
               } else {   // EPI_ADD2
-                if (g.E1) v = f4add(v, ldg4(g.E1 + o));
+                v = f4add(v, e1[i]);
                 if (g.E2) {
                   const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
                   const uint32_t rem = (uint32_t)row - img * (uint32_t)a.OHW;
@@ -512,6 +580,14 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
     }
     if (has_stats && cur_samp >= 0) flush(cur_samp);
   }
+  if (dbg_on && lane == 0) {
+    unsigned long long* o = P.dbg + warp * 8;
+    const long long t_end = clock64();
+    o[0] = (unsigned long long)(d_t1 - d_t0); o[1] = (unsigned long long)(t_end - d_t1);
+    o[2] = (unsigned long long)d_a; o[3] = (unsigned long long)d_b; o[4] = (unsigned long long)d_c; o[5] = (unsigned long long)d_n;
+    o[6] = (unsigned long long)my_tiles; o[7] = (unsigned long long)nchunks;
+  }
+#undef DBG_T
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -549,6 +625,7 @@ static bool tc_plan(tc::Params& P, size_t budget, int max_npa, int min_stage, in
   // gather path: one stage per producer warp; TMA path: spare stages hold copies in flight (up to 3 per warp)
   const int cap = P.tma ? (3 * NPROD < 16 ? 3 * NPROD : 16) : NPROD;
   if (nstage > cap) nstage = cap;
+  if (nstage > NPROD) nstage = nstage / NPROD * NPROD;      // producers cycle through whole multiples of their count
   P.nstage = nstage;
   P.nprod = nstage < NPROD ? nstage : NPROD;
   smem = fixed + (size_t)nstage * 2 * tc::STAGE_FLOATS * 4;
@@ -565,6 +642,27 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)nsplit);
+  static const bool dbg = getenv("C3D_TC_DBG") && atoi(getenv("C3D_TC_DBG")) != 0;
+  if (dbg) {      // bring-up aid: cycle counters of one CTA's warps, printed after a synchronising copy
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 32 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 32 * 8 * sizeof(unsigned long long), stream);
+    tc::Params Pd = P;
+    Pd.dbg = dbuf;
+    tc::pw_gemm_tc_kernel<NEPI, NPROD><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(Pd, tmA, tmA2);
+    unsigned long long h[32 * 8];
+    cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[tcdbg] M=%lld K=%d N=%d mode=%d epi=%d grid=%ux%u nepi=%d nprod=%d/%d nstage=%d tma=%d NpB=%d smem=%zu\n",
+            P.g.M, P.g.a.K, P.g.Ns, P.g.a.mode, P.g.epi, grid.x, grid.y, NEPI, P.nprod, NPROD, P.nstage, P.tma, P.NpB, smem);
+    for (int w = 0; w < NEPI + 1 + NPROD; ++w) {
+      const unsigned long long* o = h + w * 8;
+      const char* role = w < NEPI ? "epi " : w == NEPI ? "mma " : "prod";
+      fprintf(stderr, "[tcdbg]  w%02d %s setup=%llu total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu chunks=%llu\n", w, role,
+              o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+    }
+    return c3d_check_last(cudaGetLastError());
+  }
   tc::pw_gemm_tc_kernel<NEPI, NPROD><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(P, tmA, tmA2);
   return c3d_check_last(cudaGetLastError());
 }
@@ -583,6 +681,8 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   if (g.M * (long long)(g.a.ld > g.Ns ? g.a.ld : g.Ns) >= (1LL << 40)) return -1;
   tc::Params P;
   P.g = g;
+  P.dbg = nullptr;
+  P.rps = g.rows_per_sample >= 0x7fffffffLL ? 0x7fffffffu : (uint32_t)(g.rows_per_sample > 0 ? g.rows_per_sample : 1);
   P.lbo_is_k = lbo_is_k & 1;
   P.wait_hint = lbo_is_k >> 1;      // upper bits of the bring-up flag carry the wait hint (C3D_TC_HINT)
   P.epi_bufs = (g.epi == EPI_SWISH_BWD && g.stats) ? 2 : 1;
@@ -602,10 +702,10 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   tc::Params Pb = P, Pc = P;
   int ns_b = 0, ns_c = 0;
   size_t smem_b = 0, smem_c = 0;
-  const bool ok_b = tc_plan<8, 8>(Pb, 224 * 1024, 128, 4, ns_b, smem_b);
+  const bool ok_b = tc_plan<8, 7>(Pb, 224 * 1024, 128, 4, ns_b, smem_b);
   // two CTAs per SM: half the shared memory (minus the 1 KB the driver reserves per CTA) and half the TMEM columns
-  const bool ok_c = compact > 0 && tc_plan<4, 4>(Pc, 111 * 1024, 64, 3, ns_c, smem_c) && (long long)(g.M + tc::BM - 1) / tc::BM >= 2LL * num_sms;
-  if (ok_c && (compact >= 2 || !ok_b || ns_c <= ns_b)) return tc_launch<4, 4>(Pc, tmA, tmA2, 2 * num_sms, ns_c, smem_c, stream);
+  const bool ok_c = compact > 0 && tc_plan<4, 3>(Pc, 111 * 1024, 64, 3, ns_c, smem_c) && (long long)(g.M + tc::BM - 1) / tc::BM >= 2LL * num_sms;
+  if (ok_c && (compact >= 2 || !ok_b || ns_c <= ns_b)) return tc_launch<4, 3>(Pc, tmA, tmA2, 2 * num_sms, ns_c, smem_c, stream);
   if (!ok_b) return -1;
-  return tc_launch<8, 8>(Pb, tmA, tmA2, num_sms, ns_b, smem_b, stream);
+  return tc_launch<8, 7>(Pb, tmA, tmA2, num_sms, ns_b, smem_b, stream);
 }

@@ -8,8 +8,11 @@
 // channels) on the accumulator columns.  Accumulators (main + correction terms of the 3xTF32 split) stay in
 // TMEM for the CTA's whole pixel range; they are flushed once with fp32 atomics.
 //
-// Warps: 0-3 final epilogue (TMEM -> global atomics), 4 MMA issuer + TMEM allocation, 5-16 producers
+// Warps: 0-3 final epilogue (TMEM -> global atomics; lane 0 of warp 0 is the MMA issuer until then), 4-15 producers
 // (4 warps per pipeline stage, fused prologues identical to the GEMM kernel's).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace tcw {
@@ -19,7 +22,7 @@ using namespace tc;
 constexpr int PT = 32;                 // pixels per stage (4 MMA K-steps of 8)
 constexpr int WPS = 4;                 // producer warps per stage
 constexpr int MAX_STAGES = 3;
-constexpr int NTHREADS = (5 + WPS * MAX_STAGES) * 32;
+constexpr int NTHREADS = (4 + WPS * MAX_STAGES) * 32;      // 16 warps: 128 registers per thread
 
 struct Params {
   TileSrc big, small;      // operands after role assignment
@@ -34,6 +37,7 @@ struct Params {
   int tmem_cols;
   int desc_swap;           // bring-up switch for the MN-major LBO/SBO convention
   int big_dense, small_dense;
+  unsigned long long* dbg; // C3D_TC_DBG=1: per-warp wait/work cycle counters of one CTA, else null
 };
 
 // stage layout (floats): [big hi][big lo][small hi][small lo], each [PT/4][channels_alloc/8][8][4]
@@ -41,50 +45,45 @@ __device__ __forceinline__ size_t stage_floats(const Params& P) {
   return (size_t)2 * (P.nblocks * 32 + P.NsP / 4) * PT * 4;
 }
 
-// One call stages U work items of one operand: an item is 8 pixels x 4 channel chunks (lane = (pixel % 8, chunk)).
-// All U loads are issued before any transform so each lane keeps U (or 2U) 16-byte loads in flight.
-template <int MODE, int U>
-__device__ __forceinline__ void produce_items(const TileSrc& s, bool dense, long long M, long long row0, int it0, int it_step,
-                                              int it_end, int npg, int cgroups, float* hi, float* lo, int lane) {
-  constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
+// A producer batch = one quad of 16-byte channel chunks (16 channels; lane = (pixel % 8, chunk)) x the stage's 32
+// pixels: four float4 per lane and operand.  Loading and transforming are separate steps so the loads of the NEXT
+// batch (possibly of the next tile) are in flight while the current one is transformed: a warp always has one
+// batch of global reads outstanding, whatever the pipeline stages are doing.
+struct RawBatch { float4 v[4], v2[4]; uint32_t img[4]; };
+
+__device__ __forceinline__ void load_batch(const TileSrc& s, bool dense, long long M, long long row0, int cq, int lane, RawBatch& rb) {
+  const bool has2 = (s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS);
   const int sub = lane >> 3, pl = lane & 7;
-  float4 v[U], v2[U];
-  uint32_t img[U];
-  int kk[U], pix[U];
+  const int k = (cq * 4 + sub) * 4;
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int it = it0 + u * it_step;
-    v[u] = f4zero(); v2[u] = f4zero(); img[u] = 0; kk[u] = -1; pix[u] = 0;
-    if (it < it_end) {
-      const int cq = it / npg, pg = it - cq * npg;
-      const int k = (cq * 4 + sub) * 4;
-      pix[u] = pg * 8 + pl;
-      const long long row = row0 + pix[u];
-      if (k < s.K) {
-        kk[u] = k;
-        if (row < M) {
-          long long off, off2;
-          if (dense) { off = row * s.ld; off2 = off; img[u] = (uint32_t)row / (uint32_t)s.OHW; }
-          else row_offsets(s, (uint32_t)row, off, off2, img[u]);
-          v[u] = ldg4(s.A + off + k);
-          if (HAS2) v2[u] = ldg4(s.A2 + off2 + k);
-        } else {
-          kk[u] = -2 - k;      // row past M: store zeros at channel k
-        }
-      }
+  for (int u = 0; u < 4; ++u) {
+    const long long row = row0 + u * 8 + pl;
+    rb.v[u] = f4zero(); rb.v2[u] = f4zero(); rb.img[u] = 0;
+    if (k < s.K && row < M) {
+      long long off, off2;
+      if (dense) { off = row * s.ld; off2 = off; rb.img[u] = (uint32_t)row / (uint32_t)s.OHW; }
+      else row_offsets(s, (uint32_t)row, off, off2, rb.img[u]);
+      rb.v[u] = ldg4(s.A + off + k);
+      if (has2) rb.v2[u] = ldg4(s.A2 + off2 + k);
     }
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_batch(const TileSrc& s, long long M, long long row0, int cq, int cgroups, float* hi,
+                                            float* lo, int lane, const RawBatch& rb) {
+  const int sub = lane >> 3, pl = lane & 7;
+  const int k = (cq * 4 + sub) * 4;
+  const bool kvalid = k < s.K;
+  ChanParams cp = load_chan_params<MODE>(s, kvalid ? k : 0);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
+  for (int u = 0; u < 4; ++u) {
+    const int pix = u * 8 + pl;
     float4 x = f4zero();
-    int k = kk[u];
-    if (k >= 0) {
+    if (kvalid && row0 + pix < M) {
       float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (MODE == PRO_BN_GATE_SWISH && s.gate) g4 = ldg4(s.gate + (long long)(img[u] / (uint32_t)s.frames_per_sample) * s.ld + k);
-      const ChanParams cp = load_chan_params<MODE>(s, k);
-      x = prologue<MODE>(cp, v[u], v2[u], g4);
-    } else if (k != -1) {
-      k = -2 - k;
+      if (MODE == PRO_BN_GATE_SWISH && s.gate) g4 = ldg4(s.gate + (long long)(rb.img[u] / (uint32_t)s.frames_per_sample) * s.ld + k);
+      x = prologue<MODE>(cp, rb.v[u], rb.v2[u], g4);
     }
     // 4x4 transpose across the 4 lanes that hold 4 consecutive pixels of this channel chunk (all lanes shuffle):
     // afterwards lane j = pixel % 4 holds channel 4*chunk + j at pixels p0..p0+3
@@ -101,36 +100,34 @@ __device__ __forceinline__ void produce_items(const TileSrc& s, bool dense, long
       const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       if (odd) { x.x = r0; x.z = r1; } else { x.y = r0; x.w = r1; }
     }
-    if (k == -1) continue;
+    if (!kvalid) continue;      // channel chunks past the operand's width stay at the zeros written at kernel start
     float4 h, l;
     split4(x, h, l);
     const int ch = k + j;                                  // channel this lane now owns
-    const int o = (((pix[u] >> 2) * cgroups + (ch >> 3)) * 8 + (ch & 7)) * 4;
+    const int o = (((pix >> 2) * cgroups + (ch >> 3)) * 8 + (ch & 7)) * 4;
     *reinterpret_cast<float4*>(hi + o) = h;
     *reinterpret_cast<float4*>(lo + o) = l;
   }
 }
 
-// all items of one operand for this warp (items part, part + WPS, ...), in batches of 4
-__device__ __forceinline__ void produce_operand(const TileSrc& s, bool dense, long long M, long long row0, int part,
-                                                int nitems, int cgroups, float* hi, float* lo, int lane) {
-  constexpr int U = 4;
-  const int npg = PT / 8;
-  for (int it0 = part; it0 < nitems; it0 += U * WPS) {
-    switch (s.mode) {
-      case PRO_NONE: produce_items<PRO_NONE, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-      case PRO_BN_RELU: produce_items<PRO_BN_RELU, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-      case PRO_BN_GATE_SWISH: produce_items<PRO_BN_GATE_SWISH, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-      case PRO_BNBWD: produce_items<PRO_BNBWD, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-      case PRO_ABSDIFF: produce_items<PRO_ABSDIFF, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-      default: produce_items<PRO_MASK_POS, U>(s, dense, M, row0, it0, WPS, nitems, npg, cgroups, hi, lo, lane); break;
-    }
+__device__ __forceinline__ void store_batch_any(const TileSrc& s, long long M, long long row0, int cq, int cgroups, float* hi,
+                                                float* lo, int lane, const RawBatch& rb) {
+  switch (s.mode) {
+    case PRO_NONE: store_batch<PRO_NONE>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
+    case PRO_BN_RELU: store_batch<PRO_BN_RELU>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
+    case PRO_BN_GATE_SWISH: store_batch<PRO_BN_GATE_SWISH>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
+    case PRO_BNBWD: store_batch<PRO_BNBWD>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
+    case PRO_ABSDIFF: store_batch<PRO_ABSDIFF>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
+    default: store_batch<PRO_MASK_POS>(s, M, row0, cq, cgroups, hi, lo, lane, rb); break;
   }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == gridDim.x / 2;
+  long long d_t0 = dbg_on ? clock64() : 0, d_a = 0, d_b = 0, d_c = 0, d_n = 0;
+#define DBG_T(acc, stmt) do { if (dbg_on) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
   float* stages = reinterpret_cast<float*>(smem_raw);
   const size_t sfl = stage_floats(P);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)P.nstage * sfl);
@@ -145,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
     mbar_init(smem_u32(done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
   // zero every stage once: channel chunks beyond the operands' real width are never written by the producers
   for (size_t i = threadIdx.x; i < (size_t)P.nstage * sfl / 4; i += NTHREADS)
     reinterpret_cast<float4*>(stages)[i] = f4zero();
@@ -154,6 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long d_t1 = dbg_on ? clock64() : 0;
 
   const long long ntiles = (P.M + PT - 1) / PT;
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -161,9 +159,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
   const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
   const long long my_tiles = t_end > t_begin ? t_end - t_begin : 0;
 
-  if (warp >= 5) {
-    // ===================== producers: stage = (warp - 5) / WPS, part = (warp - 5) % WPS =====================
-    const int pw = warp - 5;
+  if (warp >= 4) {
+    // ===================== producers: stage = (warp - 4) / WPS, part = (warp - 4) % WPS =====================
+    const int pw = warp - 4;
     const int stage = pw / WPS, part = pw % WPS;
     if (stage < P.nstage) {
       float* base = stages + (size_t)stage * sfl;
@@ -172,27 +170,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
       float* small_hi = big_lo + (size_t)big_alloc * PT * 4;
       float* small_lo = small_hi + (size_t)small_alloc * PT * 4;
       const int bq = (P.big_chunks + 3) / 4, sq = (P.small_chunks + 3) / 4;    // chunk quads per operand
+      // flat cursor over this warp's batches: tiles stage, stage + nstage, ...; per tile the big operand's chunk
+      // quads part, part + WPS, ... then the small operand's
+      struct Cur { long long ti; int opnd, cq; };
+      auto normalize = [&](Cur& c) {
+        while (c.ti < my_tiles && c.cq >= (c.opnd ? sq : bq)) {
+          if (c.opnd == 0) { c.opnd = 1; c.cq = part; } else { c.opnd = 0; c.cq = part; c.ti += P.nstage; }
+        }
+      };
+      auto load = [&](const Cur& c, RawBatch& rb) {
+        const long long row0 = (t_begin + c.ti) * PT;
+        if (c.opnd == 0) load_batch(P.big, P.big_dense != 0, P.M, row0, c.cq, lane, rb);
+        else load_batch(P.small, P.small_dense != 0, P.M, row0, c.cq, lane, rb);
+      };
+      Cur nxt;
+      nxt.ti = stage; nxt.opnd = 0; nxt.cq = part;
+      normalize(nxt);
+      RawBatch cur_rb, nxt_rb;
+      if (nxt.ti < my_tiles) load(nxt, cur_rb);
       uint32_t use = 0;
       for (long long ti = stage; ti < my_tiles; ti += P.nstage, ++use) {
-        mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1);
+        DBG_T(d_a, mbar_wait(smem_u32(empty + stage), (use & 1) ^ 1));
+        ++d_n;
+        const long long t_x = dbg_on ? clock64() : 0;
         const long long row0 = (t_begin + ti) * PT;
-        produce_operand(P.big, P.big_dense != 0, P.M, row0, part, bq * (PT / 8), big_alloc / 2, big_hi, big_lo, lane);
-        produce_operand(P.small, P.small_dense != 0, P.M, row0, part, sq * (PT / 8), small_alloc / 2, small_hi, small_lo, lane);
+        while (nxt.ti == ti) {
+          const Cur c = nxt;
+          nxt.cq += WPS;
+          normalize(nxt);
+          if (nxt.ti < my_tiles) load(nxt, nxt_rb);
+          if (c.opnd == 0) store_batch_any(P.big, P.M, row0, c.cq, big_alloc / 2, big_hi, big_lo, lane, cur_rb);
+          else store_batch_any(P.small, P.M, row0, c.cq, small_alloc / 2, small_hi, small_lo, lane, cur_rb);
+          cur_rb = nxt_rb;
+        }
+        if (dbg_on) d_c += clock64() - t_x;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(full + stage));
       }
     }
-  } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else {
+    // ===================== MMA issuer: lane 0 of warp 0 (the epilogue warps have nothing to do until the end) ==========
+    if (warp == 0 && lane == 0) {
       // M = 128 (big channels), N = NsP (small channels), K = 8 pixels; both operands K-major (K = pixels)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NsP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo_big = (uint32_t)(big_alloc / 2) * 128, lbo_small = (uint32_t)(small_alloc / 2) * 128, sbo = 128;
       uint32_t first = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (long long ti = 0; ti < my_tiles; ++ti) {
-        const int stage = (int)(ti % P.nstage);
-        mbar_wait(smem_u32(full + stage), (uint32_t)(ti / P.nstage) & 1);
+        DBG_T(d_b, mbar_wait(smem_u32(full + stage), phase));
+        ++d_n;
         tc_fence_after();
         const uint32_t base = smem_u32(stages + (size_t)stage * sfl);
         const uint32_t bhi = base, blo = bhi + (uint32_t)big_alloc * PT * 16;
@@ -212,14 +240,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
           first = 1u;
         }
         umma_commit(smem_u32(empty + stage));
+        if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
       }
       umma_commit(smem_u32(done));
     }
     __syncwarp();
-  } else {
     // ===================== final epilogue: lane = big channel, columns = small channels =====================
     if (my_tiles > 0) {
-      mbar_wait(smem_u32(done), 0);
+      DBG_T(d_a, mbar_wait(smem_u32(done), 0));
       tc_fence_after();
       for (int b = 0; b < P.nblocks; ++b) {
         const int bc = b * 128 + warp * 32 + lane;          // big channel index of this thread
@@ -239,9 +267,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
       }
     }
   }
+  if (dbg_on && lane == 0) {
+    unsigned long long* o = P.dbg + warp * 8;
+    const long long t_end = clock64();
+    o[0] = (unsigned long long)(d_t1 - d_t0); o[1] = (unsigned long long)(t_end - d_t1);
+    o[2] = (unsigned long long)d_a; o[3] = (unsigned long long)d_b; o[4] = (unsigned long long)d_c; o[5] = (unsigned long long)d_n;
+    o[6] = (unsigned long long)my_tiles; o[7] = 0;
+  }
+#undef DBG_T
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
@@ -283,6 +319,7 @@ int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, floa
   if (cols > 512) return -1;
   P.tmem_cols = cols;
   P.desc_swap = desc_swap;
+  P.dbg = nullptr;
   auto dense = [](const TileSrc& s) {
     return (s.map == MAP_DENSE && s.img_stride == (long long)s.OHW * s.ld &&
             (s.A2 == nullptr || s.img_stride2 == (long long)s.OHW * s.ld)) ? 1 : 0;
@@ -300,6 +337,26 @@ int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, floa
   const long long ntiles = (M + tcw::PT - 1) / tcw::PT;
   long long gx = num_sms;
   if (gx > ntiles) gx = ntiles;
+  static const bool dbg = getenv("C3D_TC_DBG") && atoi(getenv("C3D_TC_DBG")) != 0;
+  if (dbg) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 32 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 32 * 8 * sizeof(unsigned long long), stream);
+    P.dbg = dbuf;
+    tcw::pw_wgrad_tc_kernel<<<(unsigned)gx, tcw::NTHREADS, smem, stream>>>(P);
+    unsigned long long h[32 * 8];
+    cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[wgdbg] M=%lld big=%d(mode %d) small=%d(mode %d) nblocks=%d NsP=%d nstage=%d smem=%zu\n", M, P.big.K, P.big.mode,
+            P.small.K, P.small.mode, P.nblocks, P.NsP, P.nstage, smem);
+    for (int w = 0; w < tcw::NTHREADS / 32; ++w) {
+      const unsigned long long* o = h + w * 8;
+      const char* role = w == 0 ? "mma+epi" : w < 4 ? "epi " : "prod";
+      fprintf(stderr, "[wgdbg]  w%02d %s setup=%llu total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu\n", w, role, o[0], o[1],
+              o[2], o[3], o[4], o[5], o[6]);
+    }
+    return c3d_check_last(cudaGetLastError());
+  }
   tcw::pw_wgrad_tc_kernel<<<(unsigned)gx, tcw::NTHREADS, smem, stream>>>(P);
   return c3d_check_last(cudaGetLastError());
 }

@@ -34,7 +34,8 @@ def _worker(rank, world, port, q):
         # the fused kernel's arithmetic restated on CPU: Adam on grad_scale * summed gradient
         p = opt.flat_p.clone()
         O.adam_reference_step([p], [summed / world], {}, lr=2e-4)
-        q.put((rank, local, summed, p))
+        # numpy arrays travel by value: torch tensors are shared through file descriptors that die with this process
+        q.put((rank, local.numpy(), summed.numpy(), p.detach().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -51,7 +52,7 @@ def test_two_rank_gradient_allreduce_and_update():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, l0, s0, p0), (_, l1, s1, p1) = res
+    (_, l0, s0, p0), (_, l1, s1, p1) = [(r, *(torch.from_numpy(x) for x in xs)) for r, *xs in res]
     assert torch.allclose(s0, l0 + l1) and torch.equal(s0, s1)
     assert torch.equal(p0, p1)                                   # ranks stay bit-identical
     assert not torch.equal(l0, l1)

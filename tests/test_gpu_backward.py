@@ -39,6 +39,66 @@ def test_pw_wgrad(n, k, M):
     check(f"pw_wgrad {n}x{k} M{M}", dW, ref, 3e-6)
 
 
+@pytest.mark.parametrize("T,stride,C,H,W,N,se", [(3, 1, 216, 7, 32, 3, True), (3, 1, 108, 40, 64, 2, False), (3, 1, 54, 70, 128, 2, True),
+                                                 (5, 1, 108, 9, 32, 2, True), (4, 1, 432, 6, 16, 2, False), (3, 1, 54, 6, 9, 1, True),
+                                                 (3, 2, 54, 16, 12, 2, True), (3, 1, 54, 12, 20, 2, False)])
+def test_dw_conv_backward(T, stride, C, H, W, N, se):
+    """conv_b backward through the C ABI (BN_b / SE backward transform of du, transposed depthwise conv, ReLU mask of
+    BN_a, depthwise weight gradient, BN_a backward sums) against fp64 autograd of the same formulas
+    (reference graph: model/x3d.py:184-211 conv_b -> norm_b (BN + SE) with norm_a/act_a in front)."""
+    import torch.nn.functional as F
+    from change3d_b200 import ops
+    from tests.gpu_util import ndhwc, pad_c
+    g = torch.Generator().manual_seed(T * 1000 + C + W)
+    cs = ops.pad8(C)
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    ya = torch.randn(N, C, T, H, W, generator=g)
+    w = torch.randn(C, 1, 3, 3, 3, generator=g) / 5
+    du = torch.randn(N, C, T, OH, OW, generator=g)
+    yb = torch.randn(N, C, T, OH, OW, generator=g)
+
+    def bn_block(gen):
+        mean, rstd = torch.randn(C, generator=gen) * 0.2, torch.rand(C, generator=gen) + 0.5
+        gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.3
+        blk = torch.zeros(4, cs)
+        blk[0, :C], blk[1, :C], blk[2, :C], blk[3, :C] = mean, rstd, gamma * rstd, beta
+        return blk, mean.double(), rstd.double(), (gamma * rstd).double(), beta.double()
+
+    blk_a, mean_a, rstd_a, scale_a, beta_a = bn_block(g)
+    blk_b, mean_b, rstd_b, scale_b, _ = bn_block(g)
+    coef = torch.zeros(2, cs)
+    coef[:, :C] = torch.randn(2, C, generator=g) * 0.1
+    gate = torch.rand(N, C, generator=g) + 0.2
+    dpool = torch.randn(N, C, generator=g) * 0.05
+    bc = lambda v: v.view(1, C, 1, 1, 1)                      # noqa: E731
+    bs = lambda v: v.double().view(N, C, 1, 1, 1)             # noqa: E731
+    zhat = (yb.double() - bc(mean_b)) * bc(rstd_b)
+    inner = du.double() * bs(gate) + bs(dpool) if se else du.double()
+    dy = bc(scale_b) * (inner - bc(coef[0, :C].double()) - zhat * bc(coef[1, :C].double()))
+    z = ((ya.double() - bc(mean_a)) * bc(scale_a) + bc(beta_a)).requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    out = F.conv3d(F.relu(z), wd, None, stride=(1, stride, stride), padding=1, groups=C)
+    (out * dy).sum().backward()
+    dr_ref, dw_ref = z.grad, wd.grad.view(C, 27)
+    yhat_a = (ya.double() - bc(mean_a)) * bc(rstd_a)
+    st_ref = torch.stack([dr_ref.sum(dim=(0, 2, 3, 4)), (dr_ref * yhat_a).sum(dim=(0, 2, 3, 4))])
+
+    dW = torch.zeros(C, 27, device=DEV)
+    stats = torch.zeros(2 * cs, dtype=torch.float64, device=DEV)
+    keep = [pad_c(ndhwc(du), cs).to(DEV), pad_c(ndhwc(yb), cs).to(DEV), blk_b.reshape(-1).to(DEV),
+            pad_c(gate, cs).to(DEV) if se else None, pad_c(dpool, cs).to(DEV) if se else None, coef.reshape(-1).to(DEV),
+            pad_c(ndhwc(ya), cs).to(DEV), blk_a.reshape(-1).to(DEV), w.to(DEV)]
+    dr = ops.dw_conv_bwd(*keep, C, stride, stats, dW)
+    torch.cuda.synchronize()
+    tag = f"dw_conv_bwd T{T} s{stride} C{C} W{W} se{int(se)}"
+    check(tag + " dr", dr[..., :C], ndhwc(dr_ref), 1e-5)
+    assert torch.all(dr[..., C:] == 0)
+    check(tag + " dW", dW, dw_ref, 2e-5)
+    st = stats.view(2, cs)
+    check(tag + " sum dr", st[0, :C], st_ref[0], 2e-5)
+    check(tag + " sum dr*yhat", st[1, :C], st_ref[1], 2e-5)
+
+
 def _stage_grads(stage, x, wgt, sd, dtype, depth):
     osd = O.clone_sd(sd, dtype=dtype, requires_grad=True)
     xr = x.detach().clone().to(dtype).requires_grad_(True)

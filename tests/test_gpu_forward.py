@@ -51,7 +51,12 @@ def test_pw_gemm_forward_with_stats(cin, cout, M):
 
 
 @pytest.mark.parametrize("T,stride,C,H,W,N", [(3, 1, 54, 12, 20, 2), (3, 2, 54, 16, 12, 2), (4, 1, 108, 8, 8, 1),
-                                              (5, 2, 216, 8, 12, 2), (3, 2, 24, 9, 7, 1), (5, 1, 56, 5, 6, 1)])
+                                              (5, 2, 216, 8, 12, 2), (3, 2, 24, 9, 7, 1), (5, 1, 56, 5, 6, 1),
+                                              # bench-shaped rows for the row-streaming kernel (32 / 64 / 128 wide: channel
+                                              # blocks of 32 / 16 / 8, swizzled ring), enough rows that a CTA's span crosses
+                                              # (sample, channel block) segments; odd width -> generic kernel
+                                              (3, 1, 216, 7, 32, 3), (3, 1, 108, 40, 64, 2), (3, 1, 54, 70, 128, 2),
+                                              (5, 1, 108, 9, 32, 2), (4, 1, 432, 6, 16, 2), (3, 1, 54, 6, 9, 1)])
 def test_dw_conv_forward(T, stride, C, H, W, N):
     ops = _ops()
     g = torch.Generator().manual_seed(T * 100 + C)
