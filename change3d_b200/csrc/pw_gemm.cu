@@ -302,6 +302,8 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, i
 int c3d_launch_pw_gemm_tw(const GemmArgs& g, int num_sms, cudaStream_t stream, int dbg);                   // pw_gemm_tw.cu
 int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
                            int N, int K, int num_sms, cudaStream_t stream, int desc_swap);          // pw_wgrad_tc.cu
+int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
+                           int N, int K, int num_sms, cudaStream_t stream, int swap_lbo);           // pw_wgrad_mn.cu
 
 // C3D_TC=0 forces the FFMA inner product; C3D_TC_LBO=0 swaps the LBO/SBO descriptor convention (bring-up aid).
 static int env_flag(const char* name, int dflt) {
@@ -446,6 +448,12 @@ extern "C" int c3d_pw_wgrad(const c3d_wgrad_desc* d, void* stream_) {
   fill_src(g.p, d->p);
   fill_src(g.q, d->q);
   g.M = d->M; g.dW = d->dW; g.dw_sn = d->dw_sn; g.dw_sk = d->dw_sk; g.N = d->N; g.K = d->K;
+  if (env_flag("C3D_TC", 1) && env_flag("C3D_TC_WGRAD", 1) && env_flag("C3D_TC_WMN", 1)) {
+    // dense operands: TMA-fed MN-major kernel (no transposes); C3D_TC_WMN=2 swaps the descriptor strides (bring-up)
+    const int r = c3d_launch_pw_wgrad_mn(g.p, g.q, g.M, g.dW, g.dw_sn, g.dw_sk, g.N, g.K, num_sms(), stream,
+                                         env_flag("C3D_TC_WMN", 1) == 2);
+    if (r >= 0) return r;
+  }
   if (env_flag("C3D_TC", 1) && env_flag("C3D_TC_WGRAD", 1)) {
     const int r = c3d_launch_pw_wgrad_tc(g.p, g.q, g.M, g.dW, g.dw_sn, g.dw_sk, g.N, g.K, num_sms(), stream,
                                          env_flag("C3D_TC_WSWAP", 0));

@@ -55,7 +55,7 @@ struct Params {
 // One producer warp fills one stage: 128 rows x 16 channels, lane = (row % 8, 16-byte chunk), 16 row groups.
 template <int MODE>
 __device__ __forceinline__ void produce_chunk(const Params& P, const TileSrc& s, long long row0, int chunk, float* a_hi,
-                                              float* a_lo, int lane) {
+                                              float* a_lo, int lane, int bg0, int bg1) {
   constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
   constexpr int BATCH = 8;
   const int qq = lane >> 3, rl = lane & 7;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void produce_chunk(const Params& P, const TileSrc& s,
   const float* baseA = s.A + row0 * s.ld + k;
   const float* baseA2 = HAS2 ? s.A2 + row0 * s.ld + k : nullptr;
 #pragma unroll 1
-  for (int b0 = 0; b0 < 16; b0 += BATCH) {
+  for (int b0 = bg0; b0 < bg1; b0 += BATCH) {
     float4 v[BATCH], v2[BATCH];
     uint32_t imgs[BATCH];
 #pragma unroll
@@ -142,7 +142,7 @@ __device__ __forceinline__ void produce_chunk(const Params& P, const TileSrc& s,
 // 8-row group is a per-lane constant and a warp touches each 512-byte group exactly once (conflict-free).
 template <int MODE>
 __device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& s, long long row0, int chunk, float* a_hi,
-                                                float* a_lo, int lane) {
+                                                float* a_lo, int lane, int bg0, int bg1) {
   constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
   const int qq = lane >> 3, rl = lane & 7;
   const int k = chunk * KC + 4 * qq;
@@ -168,8 +168,8 @@ __device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& 
   const bool slow_gate = (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast);
   // batches of 4 row groups: all shared-memory loads of a batch are issued before its first store (the in-place
   // stores would otherwise order every load behind the previous iteration's stores)
-#pragma unroll
-  for (int b0 = 0; b0 < 16; b0 += 4) {
+#pragma unroll 2
+  for (int b0 = bg0; b0 < bg1; b0 += 4) {
     float4 v[4], v2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -192,8 +192,9 @@ __device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& 
   }
 }
 
-template <int NEPI, int NPROD>
-__global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) pw_gemm_tc_kernel(const Params P, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2) {
+// WPS = producer warps per pipeline stage (each transforms 128 / WPS rows of the stage's chunk); CPS = CTAs per SM
+template <int NEPI, int NPROD, int WPS, int CPS>
+__global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kernel(const Params P, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2) {
   constexpr int MMA_WARP = NEPI;
   constexpr int PROD_WARP0 = NEPI + 1;
   constexpr int NTHREADS = (NEPI + 1 + NPROD) * 32;
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.nstage; ++i) {
-      mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); mbar_init(smem_u32(rawfull + i), 1);
+      mbar_init(smem_u32(full + i), WPS); mbar_init(smem_u32(empty + i), 1); mbar_init(smem_u32(rawfull + i), 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -277,7 +278,9 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
     // Chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage.  nstage is a multiple of nprod, so warp p
     // handles chunks p, p + nprod, ... and cycles through its own stages p, p + nprod, ...; (tile, chunk, stage, phase)
     // advance incrementally — no divisions in the loop.
-    const int p = warp - PROD_WARP0;
+    // with WPS > 1 the warps of a group share the group's stages; warp `half` 0 issues the TMA copies
+    const int p = (warp - PROD_WARP0) / WPS, half = (warp - PROD_WARP0) % WPS;
+    const int bg0 = half * (16 / WPS), bg1 = bg0 + 16 / WPS;          // this warp's 8-row groups of a chunk
     if (p < P.nprod && my_tiles > 0) {
       const int own = P.nstage / P.nprod;
       const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
@@ -305,24 +308,24 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
       while (cur.chunk >= nchunks) { cur.chunk -= nchunks; ++cur.ti; }
       nxt = cur;
       if (P.tma)
-        for (int i = 0; i < own - 1; ++i) { if (nxt.ti < my_tiles) issue(nxt); advance(nxt); }
+        for (int i = 0; i < own - 1; ++i) { if (nxt.ti < my_tiles && half == 0) issue(nxt); advance(nxt); }
       while (cur.ti < my_tiles) {
         float* a_hi = stages + (size_t)cur.stage * 2 * STAGE_FLOATS;
         float* a_lo = a_hi + STAGE_FLOATS;
         const long long row0 = (t_begin + cur.ti) * BM;
         if (P.tma) {
-          if (nxt.ti < my_tiles) issue(nxt);
+          if (nxt.ti < my_tiles && half == 0) issue(nxt);
           advance(nxt);
           DBG_T(d_b, mbar_wait(smem_u32(rawfull + cur.stage), cur.phase, (uint32_t)P.wait_hint));
           ++d_n;
           const long long t_x = dbg_on ? clock64() : 0;
           switch (a.mode) {
-            case PRO_NONE: transform_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_RELU: transform_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_GATE_SWISH: transform_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BNBWD: transform_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_ABSDIFF: transform_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            default: transform_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_NONE: transform_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BN_RELU: transform_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BN_GATE_SWISH: transform_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BNBWD: transform_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_ABSDIFF: transform_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            default: transform_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
           }
           if (dbg_on) d_c += clock64() - t_x;
         } else {
@@ -330,12 +333,12 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
           ++d_n;
           const long long t_x = dbg_on ? clock64() : 0;
           switch (a.mode) {
-            case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
-            default: produce_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane); break;
+            case PRO_NONE: produce_chunk<PRO_NONE>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BN_RELU: produce_chunk<PRO_BN_RELU>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BN_GATE_SWISH: produce_chunk<PRO_BN_GATE_SWISH>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_BNBWD: produce_chunk<PRO_BNBWD>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            case PRO_ABSDIFF: produce_chunk<PRO_ABSDIFF>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
+            default: produce_chunk<PRO_MASK_POS>(P, a, row0, cur.chunk, a_hi, a_lo, lane, bg0, bg1); break;
           }
           if (dbg_on) d_c += clock64() - t_x;
         }
@@ -425,6 +428,26 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
       for (int i = lane; i < 2 * P.NpA; i += 32) st[i] = 0.f;
       __syncwarp();
     };
+    // Fused epilogues read a second tensor (E1: y_b for the Swish backward, the residual gradient for the join).
+    // Those reads do not depend on the accumulator, so they run one (tile, column chunk) step ahead: the loads of
+    // the next step are in flight while this one waits for its MMAs and does its arithmetic.
+    const bool pre_e1 = g.epi != EPI_STORE && g.E1 != nullptr;
+    float4 e1n[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e1n[i] = f4zero();
+    auto prefetch_e1 = [&](long long ti_, int cc_) {
+      const long long wr0 = (t_begin + ti_) * BM + wq * 32;
+      const int cl_ = cc_ * 32 + 4 * (lane & 7);
+      const int col_ = n0 + cl_;
+      const bool ok_ = col_ < g.Ns && cl_ < NpB;
+      const float* src = g.E1 + (wr0 + (lane >> 3)) * (long long)g.Ns + col_;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        e1n[i] = (ok_ && wr0 + rr < g.M) ? ldg4(src + (long long)(4 * i) * g.Ns) : f4zero();
+      }
+    };
+    if (pre_e1 && wg < my_tiles) prefetch_e1(wg, 0);
     for (long long ti = wg; ti < my_tiles; ti += NWG) {
       const int set = (int)(ti & 1);
       const long long row0 = (t_begin + ti) * BM;
@@ -502,13 +525,13 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
               if (wsplit < 32 && wrow0 + wsplit < g.M) gt1 = ldg4(g.egate + (wsp0 + 1) * g.Ns + col);
             }
           }
-          // all global reads of the 8 row quads first (memory-level parallelism), then the arithmetic
+          // this step's E1 values were requested one step ago; request the next step's now
           float4 e1[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3);
-            e1[i] = f4zero();
-            if (g.E1 && col_ok && wrow0 + rr < g.M) e1[i] = ldg4(g.E1 + tile_o + (long long)(4 * i) * g.Ns);
+          for (int i = 0; i < 8; ++i) e1[i] = e1n[i];
+          if (pre_e1) {
+            if (cc + 1 < ncc) prefetch_e1(ti, cc + 1);
+            else if (ti + NWG < my_tiles) prefetch_e1(ti + NWG, 0);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -600,7 +623,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, (NEPI == 4 ? 2 : 1)) 
 
 // Size one kernel variant for this GEMM: N split across grid.y so that the accumulators fit `max_npa` TMEM columns
 // each and the resident weights (both halves) fit in `budget` next to >= `min_stage` pipeline stages.
-template <int NEPI, int NPROD>
+template <int NEPI, int NPROD, int WPS>
 static bool tc_plan(tc::Params& P, size_t budget, int max_npa, int min_stage, int& nsplit, size_t& smem) {
   const GemmArgs& g = P.g;
   const int K = g.a.K;
@@ -623,19 +646,20 @@ static bool tc_plan(tc::Params& P, size_t budget, int max_npa, int min_stage, in
   P.tmem_cols = cols;
   int nstage = (int)((budget - fixed) / ((size_t)2 * tc::STAGE_FLOATS * 4));
   // gather path: one stage per producer warp; TMA path: spare stages hold copies in flight (up to 3 per warp)
-  const int cap = P.tma ? (3 * NPROD < 16 ? 3 * NPROD : 16) : NPROD;
+  constexpr int NGRP = NPROD / WPS;                        // producer groups (one stage in work per group)
+  const int cap = P.tma ? (3 * NGRP < 16 ? 3 * NGRP : 16) : NGRP;
   if (nstage > cap) nstage = cap;
-  if (nstage > NPROD) nstage = nstage / NPROD * NPROD;      // producers cycle through whole multiples of their count
+  if (nstage > NGRP) nstage = nstage / NGRP * NGRP;        // producers cycle through whole multiples of their count
   P.nstage = nstage;
-  P.nprod = nstage < NPROD ? nstage : NPROD;
+  P.nprod = nstage < NGRP ? nstage : NGRP;
   smem = fixed + (size_t)nstage * 2 * tc::STAGE_FLOATS * 4;
   return true;
 }
 
-template <int NEPI, int NPROD>
+template <int NEPI, int NPROD, int WPS, int CPS>
 static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensorMap& tmA2, int ctas, int nsplit, size_t smem,
                      cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<NEPI, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<NEPI, NPROD, WPS, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return C3D_ERR_SMEM;
   const long long ntiles = (P.g.M + tc::BM - 1) / tc::BM;
   long long gx = ctas / nsplit;
@@ -649,12 +673,12 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
     cudaMemsetAsync(dbuf, 0, 32 * 8 * sizeof(unsigned long long), stream);
     tc::Params Pd = P;
     Pd.dbg = dbuf;
-    tc::pw_gemm_tc_kernel<NEPI, NPROD><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(Pd, tmA, tmA2);
+    tc::pw_gemm_tc_kernel<NEPI, NPROD, WPS, CPS><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(Pd, tmA, tmA2);
     unsigned long long h[32 * 8];
     cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
     fprintf(stderr, "[tcdbg] M=%lld K=%d N=%d mode=%d epi=%d grid=%ux%u nepi=%d nprod=%d/%d nstage=%d tma=%d NpB=%d smem=%zu\n",
-            P.g.M, P.g.a.K, P.g.Ns, P.g.a.mode, P.g.epi, grid.x, grid.y, NEPI, P.nprod, NPROD, P.nstage, P.tma, P.NpB, smem);
+            P.g.M, P.g.a.K, P.g.Ns, P.g.a.mode, P.g.epi, grid.x, grid.y, NEPI, P.nprod * WPS, NPROD, P.nstage, P.tma, P.NpB, smem);
     for (int w = 0; w < NEPI + 1 + NPROD; ++w) {
       const unsigned long long* o = h + w * 8;
       const char* role = w < NEPI ? "epi " : w == NEPI ? "mma " : "prod";
@@ -663,7 +687,7 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
     }
     return c3d_check_last(cudaGetLastError());
   }
-  tc::pw_gemm_tc_kernel<NEPI, NPROD><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(P, tmA, tmA2);
+  tc::pw_gemm_tc_kernel<NEPI, NPROD, WPS, CPS><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(P, tmA, tmA2);
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -699,13 +723,21 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
     if (ok && has2) ok = tc::make_tmap_rows(&tmA2, g.a.A2, g.a.K, g.M, g.a.ld, tc::BM);
     P.tma = ok ? 1 : 0;
   }
-  tc::Params Pb = P, Pc = P;
-  int ns_b = 0, ns_c = 0;
-  size_t smem_b = 0, smem_c = 0;
-  const bool ok_b = tc_plan<8, 7>(Pb, 224 * 1024, 128, 4, ns_b, smem_b);
+  tc::Params Pb = P, Pc = P, Ph = P;
+  int ns_b = 0, ns_c = 0, ns_h = 0;
+  size_t smem_b = 0, smem_c = 0, smem_h = 0;
+  const bool ok_b = tc_plan<8, 7, 1>(Pb, 224 * 1024, 128, 4, ns_b, smem_b);
   // two CTAs per SM: half the shared memory (minus the 1 KB the driver reserves per CTA) and half the TMEM columns
-  const bool ok_c = compact > 0 && tc_plan<4, 3>(Pc, 111 * 1024, 64, 3, ns_c, smem_c) && (long long)(g.M + tc::BM - 1) / tc::BM >= 2LL * num_sms;
-  if (ok_c && (compact >= 2 || !ok_b || ns_c <= ns_b)) return tc_launch<4, 3>(Pc, tmA, tmA2, 2 * num_sms, ns_c, smem_c, stream);
+  const bool ok_c = compact > 0 && tc_plan<4, 3, 1>(Pc, 111 * 1024, 64, 3, ns_c, smem_c) && (long long)(g.M + tc::BM - 1) / tc::BM >= 2LL * num_sms;
+  // producer-heavy shapes (a transform with transcendental / two-operand arithmetic in front of a narrow output):
+  // one epilogue warpgroup, five producer groups of two warps each.  C3D_TC_HEAVY: 0 off, 1 where the compact kernel
+  // does not apply, 2 also instead of the compact kernel, 3 for every shape (tuning aid)
+  static const int heavy_on = getenv("C3D_TC_HEAVY") ? atoi(getenv("C3D_TC_HEAVY")) : 1;
+  const bool heavy_shape = (g.a.mode == PRO_BN_GATE_SWISH || g.a.mode == PRO_BNBWD) && g.epi != EPI_SWISH_BWD && g.a.K >= 2 * g.N;
+  const bool ok_h = heavy_on && (heavy_shape || heavy_on >= 3) && tc_plan<4, 10, 2>(Ph, 224 * 1024, 128, 4, ns_h, smem_h) && (!ok_b || ns_h <= ns_b);
+  if (ok_h && heavy_on >= 2) return tc_launch<4, 10, 2, 1>(Ph, tmA, tmA2, num_sms, ns_h, smem_h, stream);
+  if (ok_c && (compact >= 2 || !ok_b || ns_c <= ns_b)) return tc_launch<4, 3, 1, 2>(Pc, tmA, tmA2, 2 * num_sms, ns_c, smem_c, stream);
+  if (ok_h) return tc_launch<4, 10, 2, 1>(Ph, tmA, tmA2, num_sms, ns_h, smem_h, stream);
   if (!ok_b) return -1;
-  return tc_launch<8, 7>(Pb, tmA, tmA2, num_sms, ns_b, smem_b, stream);
+  return tc_launch<8, 7, 1, 1>(Pb, tmA, tmA2, num_sms, ns_b, smem_b, stream);
 }

@@ -1,0 +1,403 @@
+// Weight gradient of the pointwise convolutions on tcgen05, MN-major operands fed by TMA:
+//     dW[n][k] += sum_pixels P[pix][n] * Q[pix][k]
+//
+// Pixels are the MMA K dimension.  Activations are channel-contiguous in HBM, i.e. an operand tile "32 channels x PT
+// pixels" IS the MN-major canonical UMMA layout (128-byte rows along M/N, 4 rows = one 512-byte swizzle atom along K)
+// when TMA writes it with the 128-byte swizzle of 32-byte atoms.  So the tiles go HBM -> shared by cp.async.bulk.tensor, the producer
+// warps apply the fused prologue and the TF32 hi/lo split IN PLACE (no transposes, no register staging of global
+// loads), and tcgen05.mma reads both operands with a_major = b_major = MN.
+//   stage  = [P hi | P lo | Q hi | Q lo], each [channel group of 32][PT pixels][128 B]; the raw tile lands in the hi
+//            buffer, the prologue's second tensor (y for the BN backward, the ReLU pre-activation) in the lo buffer
+//   MMA    = M 128 (a block of 4 channel groups of the wider operand) x N (the narrower operand) x K 8 pixels, three
+//            terms of the 3xTF32 split into two TMEM accumulators (main + correction) that live for the whole CTA
+//   warps  = 0-3 final epilogue (TMEM -> fp32 atomics; lane 0 of warp 0 issues the MMAs until then), 4 TMA issuer,
+//            5-15 producers (all of them work on every stage, one (operand, channel group) job at a time)
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace tcm {
+
+using namespace tc;
+
+constexpr int NPW = 11;                    // producer warps
+constexpr int NTHREADS = (5 + NPW) * 32;   // 16 warps: 128 registers per thread
+constexpr int MAX_STAGES = 6;
+
+struct Params {
+  TileSrc big, small;      // operands after role assignment (big: TMEM lanes, small: accumulator columns)
+  long long M;
+  float* dW;
+  long long dw_sb, dw_ss;  // element strides of dW along the big / small channel index
+  int Nb, Ns_;             // logical channel counts written (big, small)
+  int Gb, Gs;              // 32-channel groups staged per operand
+  int nblocks;             // 128-lane blocks of the big operand
+  int NsP;                 // accumulator columns (small channels rounded to 32)
+  int PT;                  // pixels per stage (multiple of 8)
+  int nstage;
+  int tmem_cols;
+  int swap_lbo;            // bring-up switch: exchange the LBO / SBO fields of the MN-major descriptors
+  uint32_t stage_bytes, off_blo, off_shi, off_slo, grp_bytes;
+  unsigned long long* dbg;
+};
+
+// MN-major TF32 operands have exactly one legal shared-memory layout (CUTLASS sm100_common.inl: "for mn-major tf32
+// operands, SW128_32B is the only available smem layout"): 128-byte rows of 32 consecutive M/N elements whose four
+// 32-byte chunks are XOR-swizzled with the row index mod 4 (layout type SWIZZLE_128B_BASE32B, what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); 4 K-rows form a 512-byte atom.
+// LBO = bytes between consecutive 32-element groups along M/N, SBO = bytes between 4-row groups along K.
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;       // layout_type SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// In-place prologue + hi/lo split of one (operand, channel group) job: PT rows of 128 bytes, 16-byte unit u of row r
+// at physical unit (((u >> 1) ^ (r & 3)) << 1) | (u & 1).  A lane keeps its logical unit (4 channels) for all rows; one instruction covers four
+// consecutive rows = 512 contiguous bytes, each lane its own 16 bytes (conflict-free).
+template <int MODE>
+__device__ __forceinline__ void transform_group(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
+                                                int lane) {
+  constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
+  const int u = lane & 7, rsub = lane >> 3;
+  int k = g * 32 + 4 * u;
+  const bool kvalid = k < s.K;
+  if (!kvalid) k = 0;                       // parameters are read in bounds; the columns are ignored downstream
+  const ChanParams cp = load_chan_params<MODE>(s, k);
+  float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+  int gsplit = PT;
+  bool gate_fast = true;
+  if (MODE == PRO_BN_GATE_SWISH && s.gate) {
+    const uint32_t rps = (uint32_t)s.OHW * (uint32_t)s.frames_per_sample;
+    if (rps >= (uint32_t)PT) {
+      const uint32_t samp0 = (uint32_t)row0 / rps;
+      gsplit = (int)((samp0 + 1) * rps - (uint32_t)row0);
+      g0 = ldg4(s.gate + (long long)samp0 * s.ld + k);
+      if (gsplit < PT && (long long)(samp0 + 1) * rps < M) g1 = ldg4(s.gate + (long long)(samp0 + 1) * s.ld + k);
+    } else {
+      gate_fast = false;
+    }
+  }
+  const long long left = M - row0;
+  const int nvalid = left < PT ? (int)left : PT;
+  for (int i0 = 0; i0 < PT / 4; i0 += 4) {
+    float4 v[4], v2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 4 * (i0 + i) + rsub;
+      const int o = r * 32 + (((((u >> 1) ^ (r & 3)) << 1) | (u & 1)) << 2);
+      v[i] = (i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(hi + o) : f4zero();
+      v2[i] = (HAS2 && i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(lo + o) : f4zero();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i0 + i >= PT / 4) break;
+      const int r = 4 * (i0 + i) + rsub;
+      const int o = r * 32 + (((((u >> 1) ^ (r & 3)) << 1) | (u & 1)) << 2);
+      float4 g4 = (r >= gsplit) ? g1 : g0;
+      if (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast && r < nvalid)
+        g4 = ldg4(s.gate + (long long)(((uint32_t)(row0 + r) / (uint32_t)s.OHW) / (uint32_t)s.frames_per_sample) * s.ld + k);
+      float4 x = prologue<MODE>(cp, v[i], v2[i], g4);
+      if (r >= nvalid || !kvalid) x = f4zero();      // TMA zero-fills out-of-range rows / channels: keep them zero
+      float4 h, l;
+      split4(x, h, l);
+      *reinterpret_cast<float4*>(hi + o) = h;
+      *reinterpret_cast<float4*>(lo + o) = l;
+    }
+  }
+}
+
+__device__ __forceinline__ void transform_group_any(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
+                                                    int lane) {
+  switch (s.mode) {
+    case PRO_NONE: transform_group<PRO_NONE>(s, M, row0, PT, g, hi, lo, lane); break;
+    case PRO_BN_RELU: transform_group<PRO_BN_RELU>(s, M, row0, PT, g, hi, lo, lane); break;
+    case PRO_BN_GATE_SWISH: transform_group<PRO_BN_GATE_SWISH>(s, M, row0, PT, g, hi, lo, lane); break;
+    case PRO_BNBWD: transform_group<PRO_BNBWD>(s, M, row0, PT, g, hi, lo, lane); break;
+    case PRO_ABSDIFF: transform_group<PRO_ABSDIFF>(s, M, row0, PT, g, hi, lo, lane); break;
+    default: transform_group<PRO_MASK_POS>(s, M, row0, PT, g, hi, lo, lane); break;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P, const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmB2,
+                                                                  const __grid_constant__ CUtensorMap tmS,
+                                                                  const __grid_constant__ CUtensorMap tmS2) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const bool dbg_on = P.dbg != nullptr && blockIdx.x == gridDim.x / 2;
+  long long d_t0 = dbg_on ? clock64() : 0, d_a = 0, d_b = 0, d_c = 0, d_n = 0;
+#define DBG_T(acc, stmt) do { if (dbg_on) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
+  // 1024-byte alignment of the stages (swizzle atoms): the dynamic shared window may start at any 16-byte boundary
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.nstage * P.stage_bytes);
+  uint64_t* rawfull = bars;                  // [nstage] TMA bytes have landed
+  uint64_t* full = bars + MAX_STAGES;        // [nstage] NPW producer warps have transformed the stage
+  uint64_t* empty = full + MAX_STAGES;       // [nstage] the MMAs reading the stage have retired
+  uint64_t* done = empty + MAX_STAGES;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.nstage; ++i) {
+      mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(full + i), NPW); mbar_init(smem_u32(empty + i), 1);
+    }
+    mbar_init(smem_u32(done), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const long long d_t1 = dbg_on ? clock64() : 0;
+
+  const long long ntiles = (P.M + P.PT - 1) / P.PT;
+  const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * tpc;
+  const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
+  const int my_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const uint32_t base_u32 = smem_u32(base);
+  const bool big2 = (P.big.mode == PRO_BNBWD || P.big.mode == PRO_ABSDIFF || P.big.mode == PRO_MASK_POS);
+  const bool small2 = (P.small.mode == PRO_BNBWD || P.small.mode == PRO_ABSDIFF || P.small.mode == PRO_MASK_POS);
+
+  if (warp >= 5) {
+    // ===================== producers: in-place prologue + split of (operand, channel group) jobs ====================
+    const int pw = warp - 5;
+    const int njobs = P.Gb + P.Gs;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      DBG_T(d_a, mbar_wait(smem_u32(rawfull + stage), phase));
+      ++d_n;
+      const long long t_x = dbg_on ? clock64() : 0;
+      const long long row0 = (t_begin + ti) * P.PT;
+      float* st = reinterpret_cast<float*>(base + (size_t)stage * P.stage_bytes);
+      for (int job = pw; job < njobs; job += NPW) {
+        if (job < P.Gb) {
+          float* hi = st + (size_t)job * (P.grp_bytes >> 2);
+          transform_group_any(P.big, P.M, row0, P.PT, job, hi, hi + (P.off_blo >> 2), lane);
+        } else {
+          const int g = job - P.Gb;
+          float* hi = st + (P.off_shi >> 2) + (size_t)g * (P.grp_bytes >> 2);
+          transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane);
+        }
+      }
+      if (dbg_on) d_c += clock64() - t_x;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(full + stage));
+      if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 4) {
+    // ===================== TMA issuer =====================
+    const uint32_t bytes = (uint32_t)P.PT * 128u * (uint32_t)(P.Gb * (big2 ? 2 : 1) + P.Gs * (small2 ? 2 : 1));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      DBG_T(d_a, mbar_wait(smem_u32(empty + stage), phase ^ 1u));
+      if (lane == 0) {
+        const int r0 = (int)((t_begin + ti) * P.PT);
+        const uint32_t st = base_u32 + (uint32_t)stage * P.stage_bytes;
+        const uint32_t bar = smem_u32(rawfull + stage);
+        mbar_expect_tx(bar, bytes);
+        for (int g = 0; g < P.Gb; ++g) {
+          tma_load_2d(st + (uint32_t)g * P.grp_bytes, &tmB, g * 32, r0, bar);
+          if (big2) tma_load_2d(st + P.off_blo + (uint32_t)g * P.grp_bytes, &tmB2, g * 32, r0, bar);
+        }
+        for (int g = 0; g < P.Gs; ++g) {
+          tma_load_2d(st + P.off_shi + (uint32_t)g * P.grp_bytes, &tmS, g * 32, r0, bar);
+          if (small2) tma_load_2d(st + P.off_slo + (uint32_t)g * P.grp_bytes, &tmS2, g * 32, r0, bar);
+        }
+      }
+      __syncwarp();
+      if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ===================== MMA issuer: lane 0 of warp 0 (the epilogue warps have nothing to do until the end) ==========
+    if (warp == 0 && lane == 0) {
+      // M = 128 (big channels), N = NsP (small channels), K = 8 pixels; both operands MN-major
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NsP >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo = P.swap_lbo ? 512u : P.grp_bytes, sbo = P.swap_lbo ? P.grp_bytes : 512u;
+      uint32_t first = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        DBG_T(d_b, mbar_wait(smem_u32(full + stage), phase));
+        ++d_n;
+        tc_fence_after();
+        const uint32_t st = base_u32 + (uint32_t)stage * P.stage_bytes;
+        for (int ks = 0; ks < P.PT / 8; ++ks) {
+          const uint64_t dsh = make_desc_mn128(st + P.off_shi + (uint32_t)ks * 1024u, lbo, sbo);
+          const uint64_t dsl = make_desc_mn128(st + P.off_slo + (uint32_t)ks * 1024u, lbo, sbo);
+          for (int b = 0; b < P.nblocks; ++b) {
+            const uint32_t boff = (uint32_t)b * 4u * P.grp_bytes + (uint32_t)ks * 1024u;
+            const uint64_t dbh = make_desc_mn128(st + boff, lbo, sbo), dbl = make_desc_mn128(st + P.off_blo + boff, lbo, sbo);
+            const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * P.NsP);
+            const uint32_t d_corr = d_main + (uint32_t)P.NsP;
+            umma_tf32(d_main, dbh, dsh, idesc, first);
+            umma_tf32(d_corr, dbl, dsh, idesc, first);
+            umma_tf32(d_corr, dbh, dsl, idesc, 1u);
+          }
+          first = 1u;
+        }
+        umma_commit(smem_u32(empty + stage));
+        if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(done));
+    }
+    __syncwarp();
+    // ===================== final epilogue: lane = big channel, columns = small channels =====================
+    if (my_tiles > 0) {
+      DBG_T(d_a, mbar_wait(smem_u32(done), 0));
+      tc_fence_after();
+      for (int b = 0; b < P.nblocks; ++b) {
+        const int bc = b * 128 + warp * 32 + lane;          // big channel index of this thread
+        const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * P.NsP);
+        for (int c0 = 0; c0 < P.NsP; c0 += 32) {
+          float r[32], r2[32];
+          tmem_ld32(t_main + (uint32_t)c0, r);
+          tmem_ld32(t_main + (uint32_t)(P.NsP + c0), r2);
+          if (bc < P.Nb) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int sc = c0 + j;
+              if (sc < P.Ns_) atomicAdd(P.dW + (long long)bc * P.dw_sb + (long long)sc * P.dw_ss, r[j] + r2[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (dbg_on && lane == 0) {
+    unsigned long long* o = P.dbg + warp * 8;
+    const long long t_end_ = clock64();
+    o[0] = (unsigned long long)(d_t1 - d_t0); o[1] = (unsigned long long)(t_end_ - d_t1);
+    o[2] = (unsigned long long)d_a; o[3] = (unsigned long long)d_b; o[4] = (unsigned long long)d_c; o[5] = (unsigned long long)d_n;
+    o[6] = (unsigned long long)my_tiles; o[7] = 0;
+  }
+#undef DBG_T
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// Tensor map over a row-major fp32 matrix [rows][ld] (first `inner` columns addressable): boxes of 32 columns x
+// box_rows rows land as 128-byte rows with the 128-byte swizzle.
+static bool make_tmap_mn(CUtensorMap* tm, const float* base, long long inner, long long rows, long long ld, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+    fn = (EncodeFn)p;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || inner < 4 || box_rows > 256) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tcm
+
+// Returns -1 when the shape is not handled here (caller falls back to the transposing kernel), else a C3D status.
+int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
+                           int N, int K, int num_sms, cudaStream_t stream, int swap_lbo) {
+  auto dense = [](const TileSrc& s) {
+    return s.map == MAP_DENSE && s.img_stride == (long long)s.OHW * s.ld &&
+           (s.A2 == nullptr || s.img_stride2 == (long long)s.OHW * s.ld);
+  };
+  if (!dense(p) || !dense(q)) return -1;
+  if ((p.K & 3) || (q.K & 3) || M >= (1LL << 31) || M < 256) return -1;
+  tcm::Params P;
+  const bool p_big = p.K >= q.K;
+  P.big = p_big ? p : q;
+  P.small = p_big ? q : p;
+  P.Nb = p_big ? N : K;
+  P.Ns_ = p_big ? K : N;
+  P.dw_sb = p_big ? dw_sn : dw_sk;
+  P.dw_ss = p_big ? dw_sk : dw_sn;
+  P.M = M;
+  P.dW = dW;
+  P.Gb = (P.big.K + 31) / 32;
+  P.Gs = (P.small.K + 31) / 32;
+  P.nblocks = (P.Gb + 3) / 4;
+  P.NsP = P.Gs * 32;
+  if (P.NsP > 256 || P.nblocks > 2) return -1;
+  int cols = 32;
+  while (cols < P.nblocks * 2 * P.NsP) cols <<= 1;
+  if (cols > 512) return -1;
+  P.tmem_cols = cols;
+  P.swap_lbo = swap_lbo;
+  P.dbg = nullptr;
+  // pixels per stage: larger for narrow operands (per-stage hand-off costs are fixed), bounded by shared memory;
+  // the big operand's last block may read (never use) up to 3 groups past its own: keep the small operand behind it
+  const int groups = P.Gb + P.Gs;
+  int PT = groups <= 3 ? 64 : groups <= 6 ? 32 : 16;
+  P.PT = PT;
+  P.grp_bytes = (uint32_t)PT * 128u;
+  P.off_blo = (uint32_t)P.Gb * P.grp_bytes;
+  P.off_shi = 2u * P.off_blo;
+  P.off_slo = P.off_shi + (uint32_t)P.Gs * P.grp_bytes;
+  P.stage_bytes = P.off_slo + (uint32_t)P.Gs * P.grp_bytes;
+  // the last big block reads 4 groups from its first one: stay inside the dynamic shared window
+  const uint32_t overrun = (uint32_t)(P.nblocks * 4 - P.Gb) * P.grp_bytes;
+  const size_t tail = 1024 /* alignment slack */ + 256 /* barriers */ + overrun;
+  int nstage = (int)((226 * 1024 - tail) / P.stage_bytes);
+  if (nstage > tcm::MAX_STAGES) nstage = tcm::MAX_STAGES;
+  if (nstage < 2) return -1;
+  P.nstage = nstage;
+  const size_t smem = (size_t)nstage * P.stage_bytes + tail;
+
+  CUtensorMap tmB, tmB2, tmS, tmS2;
+  memset(&tmB, 0, sizeof(tmB)); memset(&tmB2, 0, sizeof(tmB2)); memset(&tmS, 0, sizeof(tmS)); memset(&tmS2, 0, sizeof(tmS2));
+  auto has2 = [](const TileSrc& s) { return s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS; };
+  bool ok = tcm::make_tmap_mn(&tmB, P.big.A, P.big.K, M, P.big.ld, PT) && tcm::make_tmap_mn(&tmS, P.small.A, P.small.K, M, P.small.ld, PT);
+  if (ok && has2(P.big)) ok = tcm::make_tmap_mn(&tmB2, P.big.A2, P.big.K, M, P.big.ld, PT);
+  if (ok && has2(P.small)) ok = tcm::make_tmap_mn(&tmS2, P.small.A2, P.small.K, M, P.small.ld, PT);
+  if (!ok) return -1;
+
+  cudaError_t e = cudaFuncSetAttribute(tcm::pw_wgrad_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return C3D_ERR_SMEM;
+  const long long ntiles = (M + PT - 1) / PT;
+  long long gx = num_sms;
+  if (gx > ntiles) gx = ntiles;
+  static const bool dbg = getenv("C3D_TC_DBG") && atoi(getenv("C3D_TC_DBG")) != 0;
+  if (dbg) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 32 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 32 * 8 * sizeof(unsigned long long), stream);
+    P.dbg = dbuf;
+    tcm::pw_wgrad_mn_kernel<<<(unsigned)gx, tcm::NTHREADS, smem, stream>>>(P, tmB, tmB2, tmS, tmS2);
+    unsigned long long h[32 * 8];
+    cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "[wmdbg] M=%lld big=%d(mode %d) small=%d(mode %d) nblocks=%d NsP=%d PT=%d nstage=%d smem=%zu\n", M, P.big.K,
+            P.big.mode, P.small.K, P.small.mode, P.nblocks, P.NsP, PT, P.nstage, smem);
+    for (int w = 0; w < tcm::NTHREADS / 32; ++w) {
+      const unsigned long long* o = h + w * 8;
+      const char* role = w == 0 ? "mma+epi" : w < 4 ? "epi " : w == 4 ? "tma " : "prod";
+      fprintf(stderr, "[wmdbg]  w%02d %s setup=%llu total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu\n", w, role, o[0], o[1],
+              o[2], o[3], o[4], o[5], o[6]);
+    }
+    return c3d_check_last(cudaGetLastError());
+  }
+  tcm::pw_wgrad_mn_kernel<<<(unsigned)gx, tcm::NTHREADS, smem, stream>>>(P, tmB, tmB2, tmS, tmS2);
+  return c3d_check_last(cudaGetLastError());
+}
