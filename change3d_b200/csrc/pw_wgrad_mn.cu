@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
 // consecutive rows = 512 contiguous bytes, each lane its own 16 bytes (conflict-free).
 template <int MODE>
 __device__ __forceinline__ void transform_group(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
-                                                int lane) {
+                                                int lane, int q0) {      // q0: first 4-row quad of this job's 16 rows
   constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
   const int u = lane & 7, rsub = lane >> 3;
   int k = g * 32 + 4 * u;
@@ -85,7 +85,8 @@ __device__ __forceinline__ void transform_group(const TileSrc& s, long long M, l
   }
   const long long left = M - row0;
   const int nvalid = left < PT ? (int)left : PT;
-  for (int i0 = 0; i0 < PT / 4; i0 += 4) {
+  {
+    const int i0 = q0;
     float4 v[4], v2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -113,14 +114,14 @@ __device__ __forceinline__ void transform_group(const TileSrc& s, long long M, l
 }
 
 __device__ __forceinline__ void transform_group_any(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
-                                                    int lane) {
+                                                    int lane, int q0) {
   switch (s.mode) {
-    case PRO_NONE: transform_group<PRO_NONE>(s, M, row0, PT, g, hi, lo, lane); break;
-    case PRO_BN_RELU: transform_group<PRO_BN_RELU>(s, M, row0, PT, g, hi, lo, lane); break;
-    case PRO_BN_GATE_SWISH: transform_group<PRO_BN_GATE_SWISH>(s, M, row0, PT, g, hi, lo, lane); break;
-    case PRO_BNBWD: transform_group<PRO_BNBWD>(s, M, row0, PT, g, hi, lo, lane); break;
-    case PRO_ABSDIFF: transform_group<PRO_ABSDIFF>(s, M, row0, PT, g, hi, lo, lane); break;
-    default: transform_group<PRO_MASK_POS>(s, M, row0, PT, g, hi, lo, lane); break;
+    case PRO_NONE: transform_group<PRO_NONE>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    case PRO_BN_RELU: transform_group<PRO_BN_RELU>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    case PRO_BN_GATE_SWISH: transform_group<PRO_BN_GATE_SWISH>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    case PRO_BNBWD: transform_group<PRO_BNBWD>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    case PRO_ABSDIFF: transform_group<PRO_ABSDIFF>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    default: transform_group<PRO_MASK_POS>(s, M, row0, PT, g, hi, lo, lane, q0); break;
   }
 }
 
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
   if (warp >= 5) {
     // ===================== producers: in-place prologue + split of (operand, channel group) jobs ====================
     const int pw = warp - 5;
-    const int njobs = P.Gb + P.Gs;
+    const int nrc = P.PT / 16;                       // 16-row chunks per channel group
+    const int njobs = (P.Gb + P.Gs) * nrc;
     int stage = 0;
     uint32_t phase = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
@@ -179,13 +181,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       const long long row0 = (t_begin + ti) * P.PT;
       float* st = reinterpret_cast<float*>(base + (size_t)stage * P.stage_bytes);
       for (int job = pw; job < njobs; job += NPW) {
-        if (job < P.Gb) {
-          float* hi = st + (size_t)job * (P.grp_bytes >> 2);
-          transform_group_any(P.big, P.M, row0, P.PT, job, hi, hi + (P.off_blo >> 2), lane);
+        const int grp = job / nrc, q0 = (job - grp * nrc) * 4;      // (operand, channel group), 16-row chunk
+        if (grp < P.Gb) {
+          float* hi = st + (size_t)grp * (P.grp_bytes >> 2);
+          transform_group_any(P.big, P.M, row0, P.PT, grp, hi, hi + (P.off_blo >> 2), lane, q0);
         } else {
-          const int g = job - P.Gb;
+          const int g = grp - P.Gb;
           float* hi = st + (P.off_shi >> 2) + (size_t)g * (P.grp_bytes >> 2);
-          transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane);
+          transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane, q0);
         }
       }
       if (dbg_on) d_c += clock64() - t_x;
@@ -225,6 +228,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NsP >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       const uint32_t lbo = P.swap_lbo ? 512u : P.grp_bytes, sbo = P.swap_lbo ? P.grp_bytes : 512u;
+      const uint64_t tmpl = make_desc_mn128(0, lbo, sbo);      // start address (16-byte units, bits 0-13) is added per use
+      const uint32_t blk16 = (4u * P.grp_bytes) >> 4;           // descriptor units between 128-channel blocks
+      const int ksteps = P.PT / 8;
       uint32_t first = 0;
       int stage = 0;
       uint32_t phase = 0;
@@ -233,19 +239,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         ++d_n;
         tc_fence_after();
         const uint32_t st = base_u32 + (uint32_t)stage * P.stage_bytes;
-        for (int ks = 0; ks < P.PT / 8; ++ks) {
-          const uint64_t dsh = make_desc_mn128(st + P.off_shi + (uint32_t)ks * 1024u, lbo, sbo);
-          const uint64_t dsl = make_desc_mn128(st + P.off_slo + (uint32_t)ks * 1024u, lbo, sbo);
-          for (int b = 0; b < P.nblocks; ++b) {
-            const uint32_t boff = (uint32_t)b * 4u * P.grp_bytes + (uint32_t)ks * 1024u;
-            const uint64_t dbh = make_desc_mn128(st + boff, lbo, sbo), dbl = make_desc_mn128(st + P.off_blo + boff, lbo, sbo);
-            const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * P.NsP);
-            const uint32_t d_corr = d_main + (uint32_t)P.NsP;
-            umma_tf32(d_main, dbh, dsh, idesc, first);
-            umma_tf32(d_corr, dbl, dsh, idesc, first);
-            umma_tf32(d_corr, dbh, dsl, idesc, 1u);
+        uint64_t dsh = tmpl + (uint64_t)((st + P.off_shi) >> 4), dsl = tmpl + (uint64_t)((st + P.off_slo) >> 4);
+        uint64_t dbh = tmpl + (uint64_t)(st >> 4), dbl = tmpl + (uint64_t)((st + P.off_blo) >> 4);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_tf32(tmem_base, dbh, dsh, idesc, first);
+          umma_tf32(tmem_base + (uint32_t)P.NsP, dbl, dsh, idesc, first);
+          umma_tf32(tmem_base + (uint32_t)P.NsP, dbh, dsl, idesc, 1u);
+          if (P.nblocks > 1) {
+            const uint32_t d2 = tmem_base + (uint32_t)(2 * P.NsP);
+            umma_tf32(d2, dbh + blk16, dsh, idesc, first);
+            umma_tf32(d2 + (uint32_t)P.NsP, dbl + blk16, dsh, idesc, first);
+            umma_tf32(d2 + (uint32_t)P.NsP, dbh + blk16, dsl, idesc, 1u);
           }
           first = 1u;
+          dsh += 64; dsl += 64; dbh += 64; dbl += 64;           // next 8 pixels: two 512-byte atoms
         }
         umma_commit(smem_u32(empty + stage));
         if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
