@@ -238,13 +238,16 @@ def run_ours(args):
     roofline = None
     families = {}
     if not args.skip_roofline and rank == 0:
-        probe = BCDTrainStep.__new__(BCDTrainStep)
-        probe.model, probe.opt, probe.use_graph, probe.graph, probe.static, probe.loss = model, step.opt, False, None, None, None
-        probe(pre, post, tgt)                     # eager warm-up
+        # rank-local: the probe must not enter a collective (only rank 0 runs it), so it sequences the iteration
+        # and the Adam step itself instead of calling the DDP-aware BCDTrainStep.__call__
+        def probe():
+            step._iteration(pre, post, tgt)
+            step.opt.step()
+        probe()                                   # eager warm-up
         torch.cuda.synchronize()
         ops.PROF = {}
         for _ in range(2):
-            probe(pre, post, tgt)
+            probe()
         torch.cuda.synchronize()
         prof, ops.PROF = ops.PROF, None
         tot_ms = 0.0
@@ -288,6 +291,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()                                 # the other ranks wait here while rank 0 runs its probe
         dist.destroy_process_group()
 
 

@@ -242,7 +242,7 @@ extern "C" int c3d_bn_bwd_finalize(const double* stats, int groups, long long co
 }
 
 // SE backward + BN_b backward coefficients.  stats = double[N][2][Cs]: per-sample (sum du, sum du*zhat).
-__global__ void __launch_bounds__(256) se_bn_bwd_finalize_kernel(
+__global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     const double* __restrict__ stats, int N, long long cnt, const float* __restrict__ bnp, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ gate, const float* __restrict__ hidden,
     const float* __restrict__ zhat_mean, const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cs, int R,
@@ -251,11 +251,11 @@ __global__ void __launch_bounds__(256) se_bn_bwd_finalize_kernel(
   extern __shared__ float sm[];
   float* dps = sm;               // [N][C]   grad wrt pre-sigmoid
   float* dpr = sm + (size_t)N * C;   // [N][R]   grad wrt pre-relu
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const bool se = (gate != nullptr);
   const double Mtot = (double)cnt * (double)N;
   if (se) {
-    for (int i = tid; i < N * C; i += 256) {
+    for (int i = tid; i < N * C; i += nthr) {
       const int n = i / C, c = i - n * C;
       const double A = stats[((long long)n * 2) * Cs + c], Bz = stats[((long long)n * 2 + 1) * Cs + c];
       const float g = gate[(long long)n * Cs + c];
@@ -263,19 +263,19 @@ __global__ void __launch_bounds__(256) se_bn_bwd_finalize_kernel(
       dps[i] = dg * g * (1.f - g);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
+    for (int c = tid; c < C; c += nthr) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += dps[n * C + c];
       db2[c] = s;
     }
-    for (int i = tid; i < C * R; i += 256) {
+    for (int i = tid; i < C * R; i += nthr) {
       const int c = i / R, r = i - c * R;
       float s = 0.f;
       for (int n = 0; n < N; ++n) s = fmaf(dps[n * C + c], hidden[(long long)n * R + r], s);
       dw2[i] = s;
     }
     const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < N * R; i += 8) {
+    for (int i = warp; i < N * R; i += (nthr >> 5)) {
       const int n = i / R, r = i - n * R;
       float s = 0.f;
       for (int c = lane; c < C; c += 32) s = fmaf(w2[c * R + r], dps[n * C + c], s);
@@ -284,19 +284,19 @@ __global__ void __launch_bounds__(256) se_bn_bwd_finalize_kernel(
       if (lane == 0) dpr[i] = hidden[(long long)n * R + r] > 0.f ? s : 0.f;
     }
     __syncthreads();
-    for (int r = tid; r < R; r += 256) {
+    for (int r = tid; r < R; r += nthr) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += dpr[n * R + r];
       db1[r] = s;
     }
-    for (int i = tid; i < R * C; i += 256) {
+    for (int i = tid; i < R * C; i += nthr) {
       const int r = i / C, c = i - r * C;
       float s = 0.f;
       for (int n = 0; n < N; ++n) s = fmaf(dpr[n * R + r], fmaf(zhat_mean[(long long)n * Cs + c], gamma[c], beta[c]), s);
       dw1[i] = s;
     }
   }
-  for (int c = tid; c < Cs; c += 256) {
+  for (int c = tid; c < Cs; c += nthr) {
     double S1 = 0.0, S2 = 0.0;
     if (c < C) {
       for (int n = 0; n < N; ++n) {
@@ -333,7 +333,7 @@ extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long coun
   size_t smem = gate ? ((size_t)N * C + (size_t)N * R) * sizeof(float) : 0;
   if (smem > 200 * 1024) return C3D_ERR_SMEM;
   cudaFuncSetAttribute(se_bn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  se_bn_bwd_finalize_kernel<<<1, 256, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, bnp, gamma, beta, gate,
+  se_bn_bwd_finalize_kernel<<<1, 1024, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, bnp, gamma, beta, gate,
                                                                     hidden, zhat_mean, w1, w2, C, Cs, R, coef, dgamma,
                                                                     dbeta, dpool, dw1, db1, dw2, db2);
   return c3d_check_last(cudaGetLastError());
