@@ -393,7 +393,8 @@ static int launch_dw_bwd(const float* du, const float* yb, const float* bnp_b, c
 }
 
 int c3d_launch_dw_bwd_ring(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW,
-                           double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st);   // dw_ring.cu
+                           double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st, const float* yb,
+                           const float* bnp_b, const float* gate, const float* dpool, const float* coef_b);   // dw_ring.cu
 
 extern "C" int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, const float* gate,
                                const float* dpool, const float* coef_b, const float* y_a, const float* bnp_a,
@@ -409,6 +410,11 @@ extern "C" int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, 
   // with 4 / 2 channels per thread (kept for comparison, scratch/bench_dw.py)
   const int variant = dw_env("C3D_DW_BWD", 0);
   int r = -1;
+  if (variant == 0 && stride == 1 && dw_env("C3D_DW_FUSE", 1)) {
+    // row-streaming kernel with the BN_b / SE backward transform of du fused into its ring fill (du is left untouched)
+    const int rr = c3d_launch_dw_bwd_ring(du, y_a, bnp_a, w, dr, dW, stats_a, N, T, IH, IW, C, Cs, st, y_b, bnp_b, gate, dpool, coef_b);
+    if (rr >= 0) return rr;
+  }
   if ((variant == 0 || variant == 3) && Cs / 2 <= 128) {
     const int OH = (IH - 1) / stride + 1, OW = (IW - 1) / stride + 1;
     const long long total4 = (long long)N * T * OH * OW * (Cs >> 2);
@@ -417,7 +423,7 @@ extern "C" int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, 
     dw_dy_kernel<<<(unsigned)blocks, 256, 0, st>>>(du, y_b, bnp_b, gate, dpool, coef_b, total4, Cs, (long long)T * OH * OW);
     if (cudaGetLastError() != cudaSuccess) return C3D_ERR_CUDA;
     if (stride == 1) {          // row-streaming kernel over the pre-computed dy
-      const int rr = c3d_launch_dw_bwd_ring(du, y_a, bnp_a, w, dr, dW, stats_a, N, T, IH, IW, C, Cs, st);
+      const int rr = c3d_launch_dw_bwd_ring(du, y_a, bnp_a, w, dr, dW, stats_a, N, T, IH, IW, C, Cs, st, nullptr, nullptr, nullptr, nullptr, nullptr);
       if (rr >= 0) return rr;
     }
     if (variant == 3 && T == 3)

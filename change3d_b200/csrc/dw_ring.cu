@@ -36,6 +36,7 @@ struct Geo {
   int N, IH, IW, C, Cs;
   int nCB, nSEG;       // channel blocks, column strips
   int R, D;            // ring slots, rows requested ahead of the computed row (R >= D + 4)
+  int R2;              // slots of the second ring of the fused backward (D + 2)
   long long total_steps, steps_per_cta;
 };
 
@@ -262,16 +263,30 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restr
 // the thread's own pixels and is read straight from global memory while the row's ring data is awaited.  The 27
 // weight-gradient accumulators of the thread's channel stay in registers for a whole unit.
 // ------------------------------------------------------------------------------------------------
-template <int T>
+// FUSED: DY is the raw gradient du of the Swish input and the BN_b / SE backward transform
+//     dy = scale_b * (du * gate + dpool - c1 - zhat_b * c2),  zhat_b = (y_b - mean_b) * rstd_b
+// is applied in place to each ring piece by the thread that requested it (y_b pieces land in a small second ring),
+// which removes the elementwise pre-pass over du / y_b.
+struct FuseArgs {
+  const float* YB;       // raw conv_b output
+  const float* bnp_b;    // [4][Cs]
+  const float* gate;     // [N][Cs] or null
+  const float* dpool;    // [N][Cs] or null
+  const float* coef_b;   // [2][Cs]
+};
+
+template <int T, bool FUSED>
 __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restrict__ DY, const float* __restrict__ YA,
                                                             const float* __restrict__ bnp_a, const float* __restrict__ w,
                                                             float* __restrict__ DR, float* __restrict__ dW,
-                                                            double* __restrict__ stats_a, const Geo G) {
+                                                            double* __restrict__ stats_a, const Geo G, const FuseArgs F) {
   constexpr int SF = T * TS;
   extern __shared__ __align__(16) float sm[];
   float* ring = sm;                                                  // [R][T][PIX][CB]
-  float* s_dw = ring + (size_t)G.R * SF;                             // [27][CB]
+  float* ring2 = ring + (size_t)G.R * SF;                            // [R2][T][PIX][CB] y_b pieces (FUSED)
+  float* s_dw = ring2 + (size_t)(FUSED ? G.R2 : 0) * SF;             // [27][CB]
   double* s_st = reinterpret_cast<double*>(s_dw + 28 * CB);          // [2][CB]
+  float* s_cb = reinterpret_cast<float*>(s_st + 2 * CB);             // [7][CB] scale, gate, dpool, c1, mean, rstd, c2 (FUSED)
   const int tid = threadIdx.x;
   const int cl = tid & 31, grp = tid >> 5;
   const uint32_t ring_u32 = smem_u32(ring);
@@ -304,7 +319,19 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
       mean_a = __ldg(bnp_a + c); rstd_a = __ldg(bnp_a + G.Cs + c);
       scale_a = __ldg(bnp_a + 2 * G.Cs + c); beta_a = __ldg(bnp_a + 3 * G.Cs + c);
     }
+    if (FUSED && tid < CB) {
+      const int cc = c0 + tid;
+      const bool ok = cc < G.Cs;
+      s_cb[0 * CB + tid] = ok ? __ldg(F.bnp_b + 2 * G.Cs + cc) : 0.f;                                   // scale_b
+      s_cb[1 * CB + tid] = (ok && F.gate) ? __ldg(F.gate + (long long)u.n * G.Cs + cc) : 1.f;
+      s_cb[2 * CB + tid] = (ok && F.gate) ? __ldg(F.dpool + (long long)u.n * G.Cs + cc) : 0.f;
+      s_cb[3 * CB + tid] = ok ? __ldg(F.coef_b + cc) : 0.f;                                             // c1
+      s_cb[4 * CB + tid] = ok ? __ldg(F.bnp_b + cc) : 0.f;                                              // mean_b
+      s_cb[5 * CB + tid] = ok ? __ldg(F.bnp_b + G.Cs + cc) : 0.f;                                       // rstd_b
+      s_cb[6 * CB + tid] = ok ? __ldg(F.coef_b + G.Cs + cc) : 0.f;                                      // c2
+    }
     const float* DYu = DY + (long long)u.n * T * img + (long long)(seg_start - 1) * G.Cs + c0;
+    const float* YBu = FUSED ? F.YB + (long long)u.n * T * img + (long long)(seg_start - 1) * G.Cs + c0 : nullptr;
     const long long toff_g = (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 4 * grp) * G.Cs + c;
     const float* YAt = YA + toff_g;                   // frame 0, row r0, this thread's first column
     float* DRt = DR + toff_g;
@@ -313,25 +340,60 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
     if (!c_ok) nvalid = 0;
     double st_s = 0.0, st_t = 0.0;
 
-    int issue_row = u.r0 - 1, issue_slot = 0;
+    int issue_row = u.r0 - 1, issue_slot = 0, issue_slot2 = 0;
     auto issue = [&]() {
       const bool row_ok = issue_row >= 0 && issue_row < G.IH;
       const uint32_t dst0 = ring_u32 + (uint32_t)(issue_slot * SF) * 4;
+      const uint32_t dst2 = ring_u32 + (uint32_t)((G.R + issue_slot2) * SF) * 4;
       const float* src0 = DYu + (long long)issue_row * rowstride;
+      const float* src2 = FUSED ? YBu + (long long)issue_row * rowstride : nullptr;
 #pragma unroll
       for (int i = 0; i < Pieces<T>::NE; ++i) {
         if (pc.exists >> i & 1) {
           const bool ok = row_ok && (pc.ok >> i & 1);
           cp_async16(dst0 + (uint32_t)pc.s_off[i] * 4, ok ? (const void*)(src0 + pc.g_off[i]) : (const void*)DY, ok ? 16u : 0u);
+          if (FUSED && ok) cp_async16(dst2 + (uint32_t)pc.s_off[i] * 4, (const void*)(src2 + pc.g_off[i]), 16u);
         }
       }
       cp_async_commit();
       ++issue_row;
       if (++issue_slot == G.R) issue_slot = 0;
+      if (FUSED && ++issue_slot2 == G.R2) issue_slot2 = 0;
+    };
+    // FUSED: du -> dy in place on this thread's own pieces (same formula and operation order as dw_dy_kernel)
+    auto transform = [&](int row, int slot, int slot2) {
+      if (!FUSED || row < 0 || row >= G.IH) return;
+      float* base = ring + (size_t)slot * SF;
+      const float* base2 = ring2 + (size_t)slot2 * SF;
+      const int c4 = (tid & 7) * 4;                    // NT is a multiple of 8: every piece of a thread has this quad
+      const float4 scale = *reinterpret_cast<const float4*>(s_cb + 0 * CB + c4), g = *reinterpret_cast<const float4*>(s_cb + 1 * CB + c4);
+      const float4 dp = *reinterpret_cast<const float4*>(s_cb + 2 * CB + c4), c1 = *reinterpret_cast<const float4*>(s_cb + 3 * CB + c4);
+      const float4 mean = *reinterpret_cast<const float4*>(s_cb + 4 * CB + c4), rstd = *reinterpret_cast<const float4*>(s_cb + 5 * CB + c4);
+      const float4 c2 = *reinterpret_cast<const float4*>(s_cb + 6 * CB + c4);
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.ok >> i & 1) {
+          float4* p = reinterpret_cast<float4*>(base + pc.s_off[i]);
+          const float4 d = *p, y = *reinterpret_cast<const float4*>(base2 + pc.s_off[i]);
+          float4 o;
+          o.x = scale.x * (fmaf(d.x, g.x, dp.x) - c1.x - (y.x - mean.x) * rstd.x * c2.x);
+          o.y = scale.y * (fmaf(d.y, g.y, dp.y) - c1.y - (y.y - mean.y) * rstd.y * c2.y);
+          o.z = scale.z * (fmaf(d.z, g.z, dp.z) - c1.z - (y.z - mean.z) * rstd.z * c2.z);
+          o.w = scale.w * (fmaf(d.w, g.w, dp.w) - c1.w - (y.w - mean.w) * rstd.w * c2.w);
+          *p = o;
+        }
+      }
     };
 
     for (int i = 0; i < G.D + 2; ++i) issue();
-    int sl = 0;                                       // slot of row ih - 1
+    int sl = 0, sq = 0;                               // slot of row ih - 1; second-ring slot of row ih + 1
+    if (FUSED) {
+      __syncthreads();                                // s_cb is visible
+      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      transform(u.r0 - 1, 0, 0);
+      transform(u.r0, 1, 1);
+      sq = 2;
+    }
     for (int ih = u.r0; ih < u.r1; ++ih) {
       issue();
       // this thread's own y_a values: in flight while the ring row is awaited
@@ -343,6 +405,8 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
       if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
       const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
       const int sl2 = sl1 + 1 >= G.R ? sl1 + 1 - G.R : sl1 + 1;
+      transform(ih + 1, sl2, sq);
+      if (FUSED && ++sq == G.R2) sq = 0;
       __syncthreads();
       if (nvalid > 0) {
         const int toff = (4 * grp) * CB + cl;
@@ -430,7 +494,8 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-static bool plan(Geo& G, int T, int N, int IH, int IW, int C, int Cs, size_t extra_smem, size_t& smem, int& grid, int ctas_per_sm) {
+static bool plan(Geo& G, int T, int N, int IH, int IW, int C, int Cs, size_t extra_smem, size_t& smem, int& grid, int ctas_per_sm,
+                 bool second_ring = false) {
   if (IW < 1 || (Cs & 3) || T < 3 || T > 5) return false;
   if ((long long)T * IH * IW * Cs >= (1LL << 31)) return false;        // per-sample offsets are 32-bit
   G.N = N; G.IH = IH; G.IW = IW; G.C = C; G.Cs = Cs;
@@ -442,10 +507,10 @@ static bool plan(Geo& G, int T, int N, int IH, int IW, int C, int Cs, size_t ext
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t budget = (size_t)(max_smem + 1024) / ctas_per_sm - 1024;
-  G.D = 2; G.R = 6;
-  if (G.R * slot + extra_smem > budget) { G.D = 1; G.R = 5; }
-  if (G.R * slot + extra_smem > budget) return false;
-  smem = G.R * slot + extra_smem;
+  G.D = 2; G.R = 6; G.R2 = second_ring ? G.D + 2 : 0;
+  if ((G.R + G.R2) * slot + extra_smem > budget) { G.D = 1; G.R = 5; G.R2 = second_ring ? G.D + 2 : 0; }
+  if ((G.R + G.R2) * slot + extra_smem > budget) return false;
+  smem = (G.R + G.R2) * slot + extra_smem;
   G.total_steps = (long long)N * G.nCB * G.nSEG * IH;
   long long g = (long long)sms * ctas_per_sm;
   if (g > G.total_steps) g = G.total_steps;
@@ -486,32 +551,41 @@ int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, flo
   return c3d_check_last(cudaGetLastError());
 }
 
-// dy = du already transformed by the elementwise pre-pass (dw_dy_kernel).  Returns -1 when not handled here.
+// fuse == nullptr: dy = du already transformed by the elementwise pre-pass (dw_dy_kernel); else the raw du plus the
+// BN_b / SE backward operands (transform fused into the ring fill).  Returns -1 when not handled here.
+template <int T>
+static int launch_bwd(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW, double* stats_a,
+                      const dwr::Geo& G, const dwr::FuseArgs* fuse, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (fuse) {
+    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return C3D_ERR_SMEM;
+    dwr::dw_bwd_ring_kernel<T, true><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G, *fuse);
+  } else {
+    dwr::FuseArgs none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return C3D_ERR_SMEM;
+    dwr::dw_bwd_ring_kernel<T, false><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G, none);
+  }
+  return c3d_check_last(cudaGetLastError());
+}
+
 int c3d_launch_dw_bwd_ring(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW,
-                           double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st) {
+                           double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st, const float* yb,
+                           const float* bnp_b, const float* gate, const float* dpool, const float* coef_b) {
   if (!dwr::env_int("C3D_DW_RING", 1)) return -1;
   dwr::Geo G;
   size_t smem = 0;
   int grid = 0;
-  const size_t extra = (size_t)(28 * dwr::CB * 4 + 2 * dwr::CB * 8);       // s_dw [27][CB] floats (+ pad) + s_st [2][CB] doubles
-  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1)) return -1;
-  cudaError_t e;
+  const bool fused = yb != nullptr;
+  // s_dw [27][CB] floats (+ pad) + s_st [2][CB] doubles + s_cb [7][CB] floats
+  const size_t extra = (size_t)(28 * dwr::CB * 4 + 2 * dwr::CB * 8 + 8 * dwr::CB * 4);
+  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1, fused)) return -1;
+  dwr::FuseArgs F = {yb, bnp_b, gate, dpool, coef_b};
+  const dwr::FuseArgs* fp = fused ? &F : nullptr;
   switch (T) {
-    case 3:
-      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_bwd_ring_kernel<3><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
-      break;
-    case 4:
-      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_bwd_ring_kernel<4><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
-      break;
-    default:
-      e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_bwd_ring_kernel<5><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
-      break;
+    case 3: return launch_bwd<3>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+    case 4: return launch_bwd<4>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+    default: return launch_bwd<5>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
   }
-  return c3d_check_last(cudaGetLastError());
 }
