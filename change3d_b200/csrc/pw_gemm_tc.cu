@@ -525,78 +525,146 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
               if (wsplit < 32 && wrow0 + wsplit < g.M) gt1 = ldg4(g.egate + (wsp0 + 1) * g.Ns + col);
             }
           }
-          // this step's E1 values were requested one step ago; request the next step's now
-          float4 e1[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e1[i] = e1n[i];
+          // This step's E1 values were requested one step ago (e1n).  The next step's are requested quad by quad right
+          // after the matching quad has been consumed, so no second register copy of the 8 quads is needed.
+          long long nti = -1;
+          int ncc_next = 0;
           if (pre_e1) {
-            if (cc + 1 < ncc) prefetch_e1(ti, cc + 1);
-            else if (ti + NWG < my_tiles) prefetch_e1(ti + NWG, 0);
+            if (cc + 1 < ncc) { nti = ti; ncc_next = cc + 1; }
+            else if (ti + NWG < my_tiles) { nti = ti + NWG; ncc_next = 0; }
           }
+          const long long nwr0 = nti >= 0 ? (t_begin + nti) * BM + wq * 32 : 0;
+          const int ncl = ncc_next * 32 + 4 * (lane & 7);
+          const bool nok = nti >= 0 && n0 + ncl < g.Ns && ncl < NpB;
+          const float* nsrc = pre_e1 ? g.E1 + (nwr0 + (lane >> 3)) * (long long)g.Ns + n0 + ncl : nullptr;
+#define E1_TAKE(i, dst)                                                                                          \
+          const float4 dst = e1n[i];                                                                            \
+          e1n[i] = (nok && nwr0 + 4 * (i) + (lane >> 3) < g.M) ? ldg4(nsrc + (long long)(4 * (i)) * g.Ns) : f4zero();
+          // the staged accumulator rows first: all shared loads issue back to back and the 8 row quads below are
+          // independent instruction streams (no shared-memory stores between them)
+          float4 vv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3);
-            const long long row = wrow0 + rr;
-            float4 v = *reinterpret_cast<const float4*>(S + rr * EPI_LD + 4 * q);
-            float4 v2 = f4zero();
-            if (row < g.M && col_ok) {
-              const long long o = tile_o + (long long)(4 * i) * g.Ns;
-              if (g.epi == EPI_SWISH_BWD) {
-                const float4 yb = e1[i];
-                long long sp = rr >= wsplit ? wsp0 + 1 : wsp0;
-                float4 gt = rr >= wsplit ? gt1 : gt0;
-                if (!sp_fast) {
-                  sp = (long long)((uint32_t)row / P.rps);
-                  if (g.egate) gt = ldg4(g.egate + sp * g.Ns + col);
+          for (int i = 0; i < 8; ++i) vv[i] = *reinterpret_cast<const float4*>(S + (4 * i + (lane >> 3)) * EPI_LD + 4 * q);
+          if (g.epi == EPI_SWISH_BWD && sp_fast) {
+            // per-lane partial sums of (du, du * zhat) for the warp's first sample (a0, z0) and, when its 32 rows
+            // straddle a sample boundary, the next one (a1, z1)
+            float4 a0 = f4zero(), z0 = f4zero(), a1 = f4zero(), z1 = f4zero();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const bool valid = col_ok && wrow0 + rr < g.M;
+              const bool second = rr >= wsplit;
+              E1_TAKE(i, yb)
+              const float4 gt = second ? gt1 : gt0, acc = vv[i];
+              float4 du, dz;
+              {
+                const float xc = yb.x - mean.x, zh = xc * rstd.x, u = fmaf(xc, scale.x, beta.x) * gt.x;
+                du.x = acc.x * swish_gradf_(u); dz.x = du.x * zh;
+              }
+              {
+                const float xc = yb.y - mean.y, zh = xc * rstd.y, u = fmaf(xc, scale.y, beta.y) * gt.y;
+                du.y = acc.y * swish_gradf_(u); dz.y = du.y * zh;
+              }
+              {
+                const float xc = yb.z - mean.z, zh = xc * rstd.z, u = fmaf(xc, scale.z, beta.z) * gt.z;
+                du.z = acc.z * swish_gradf_(u); dz.z = du.z * zh;
+              }
+              {
+                const float xc = yb.w - mean.w, zh = xc * rstd.w, u = fmaf(xc, scale.w, beta.w) * gt.w;
+                du.w = acc.w * swish_gradf_(u); dz.w = du.w * zh;
+              }
+              if (valid) {
+                st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, du);
+                if (second) { a1 = f4add(a1, du); z1 = f4add(z1, dz); } else { a0 = f4add(a0, du); z0 = f4add(z0, dz); }
+              }
+            }
+            if (has_stats) {
+              // fold the four lanes that share a column quad (lanes q, q + 8, q + 16, q + 24)
+              auto fold = [](float4& t) {
+                t.x += __shfl_xor_sync(0xffffffffu, t.x, 8); t.y += __shfl_xor_sync(0xffffffffu, t.y, 8);
+                t.z += __shfl_xor_sync(0xffffffffu, t.z, 8); t.w += __shfl_xor_sync(0xffffffffu, t.w, 8);
+                t.x += __shfl_xor_sync(0xffffffffu, t.x, 16); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16);
+                t.z += __shfl_xor_sync(0xffffffffu, t.z, 16); t.w += __shfl_xor_sync(0xffffffffu, t.w, 16);
+              };
+              fold(a0); fold(z0);
+              if (!straddle) {
+                if (lane < 8) {
+                  float* s1 = st + cc * 32 + 4 * q;
+                  float* s2 = st + P.NpA + cc * 32 + 4 * q;
+                  s1[0] += a0.x; s1[1] += a0.y; s1[2] += a0.z; s1[3] += a0.w;
+                  s2[0] += z0.x; s2[1] += z0.y; s2[2] += z0.z; s2[3] += z0.w;
                 }
+              } else {       // tile straddles two samples: this warp's sums go straight to the global statistics
+                fold(a1); fold(z1);
+                if (lane < 8 && col_ok) {
+                  double* d0 = g.stats + (wsp0 * 2) * g.Ns + col;
+                  atomicAdd(d0 + 0, (double)a0.x); atomicAdd(d0 + 1, (double)a0.y); atomicAdd(d0 + 2, (double)a0.z); atomicAdd(d0 + 3, (double)a0.w);
+                  atomicAdd(d0 + g.Ns + 0, (double)z0.x); atomicAdd(d0 + g.Ns + 1, (double)z0.y);
+                  atomicAdd(d0 + g.Ns + 2, (double)z0.z); atomicAdd(d0 + g.Ns + 3, (double)z0.w);
+                  if (wsplit < 32 && wrow0 + wsplit < g.M) {
+                    double* d1 = d0 + 2 * g.Ns;
+                    atomicAdd(d1 + 0, (double)a1.x); atomicAdd(d1 + 1, (double)a1.y); atomicAdd(d1 + 2, (double)a1.z); atomicAdd(d1 + 3, (double)a1.w);
+                    atomicAdd(d1 + g.Ns + 0, (double)z1.x); atomicAdd(d1 + g.Ns + 1, (double)z1.y);
+                    atomicAdd(d1 + g.Ns + 2, (double)z1.z); atomicAdd(d1 + g.Ns + 3, (double)z1.w);
+                  }
+                }
+              }
+            }
+          } else if (g.epi == EPI_SWISH_BWD) {
+            // samples shorter than a warp's 32 rows (tiny images): per-element statistics atomics
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const long long row = wrow0 + rr;
+              if (row < g.M && col_ok) {
+                const long long sp = (long long)((uint32_t)row / P.rps);
+                float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (g.egate) gt = ldg4(g.egate + sp * g.Ns + col);
+                const float4 yb = e1n[i];
                 float yv[4] = {yb.x, yb.y, yb.z, yb.w}, mv[4] = {mean.x, mean.y, mean.z, mean.w};
                 float rv[4] = {rstd.x, rstd.y, rstd.z, rstd.w}, sv[4] = {scale.x, scale.y, scale.z, scale.w};
                 float bv[4] = {beta.x, beta.y, beta.z, beta.w}, gv[4] = {gt.x, gt.y, gt.z, gt.w};
-                float av[4] = {v.x, v.y, v.z, v.w}, du[4], dz[4];
+                float av[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w}, du[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float xc = yv[j] - mv[j];
                   const float zh = xc * rv[j];
                   const float u = fmaf(xc, sv[j], bv[j]) * gv[j];
                   du[j] = av[j] * swish_gradf_(u);
-                  dz[j] = du[j] * zh;
-                  if (straddle && has_stats) {
+                  if (has_stats) {
                     atomicAdd(g.stats + (sp * 2 + 0) * g.Ns + col + j, (double)du[j]);
-                    atomicAdd(g.stats + (sp * 2 + 1) * g.Ns + col + j, (double)dz[j]);
+                    atomicAdd(g.stats + (sp * 2 + 1) * g.Ns + col + j, (double)(du[j] * zh));
                   }
                 }
-                v = make_float4(du[0], du[1], du[2], du[3]);
-                v2 = make_float4(dz[0], dz[1], dz[2], dz[3]);
-                st4(g.Y + o, v);
-              } else {   // EPI_ADD2
-                v = f4add(v, e1[i]);
-                if (g.E2) {
-                  const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
-                  const uint32_t rem = (uint32_t)row - img * (uint32_t)a.OHW;
-                  const uint32_t oh = rem / (uint32_t)a.OW, ow = rem - oh * (uint32_t)a.OW;
-                  if (!(oh & 1) && !(ow & 1)) {
-                    const long long hr = (long long)img * (a.OHW >> 2) + (long long)(oh >> 1) * (a.OW >> 1) + (ow >> 1);
-                    v = f4add(v, ldg4(g.E2 + hr * g.Ns + col));
-                  }
-                }
-                st4(g.Y + o, v);
+                st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, make_float4(du[0], du[1], du[2], du[3]));
               }
-            } else {
-              v = f4zero();
             }
-            if (has_stats) {
-              *reinterpret_cast<float4*>(S + rr * EPI_LD + 4 * q) = v;
-              *reinterpret_cast<float4*>(S2 + rr * EPI_LD + 4 * q) = v2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { E1_TAKE(i, unused_) (void)unused_; }
+          } else {   // EPI_ADD2: residual join (+ the stride-2 shortcut gradient at even pixels)
+            float4 e2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e2[i] = f4zero();
+              const long long row = wrow0 + 4 * i + (lane >> 3);
+              if (g.E2 && col_ok && row < g.M) {
+                const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
+                const uint32_t rem = (uint32_t)row - img * (uint32_t)a.OHW;
+                const uint32_t oh = rem / (uint32_t)a.OW, ow = rem - oh * (uint32_t)a.OW;
+                if (!(oh & 1) && !(ow & 1)) {
+                  const long long hr = (long long)img * (a.OHW >> 2) + (long long)(oh >> 1) * (a.OW >> 1) + (ow >> 1);
+                  e2[i] = ldg4(g.E2 + hr * g.Ns + col);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              E1_TAKE(i, res)
+              if (col_ok && wrow0 + 4 * i + (lane >> 3) < g.M)
+                st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, f4add(f4add(vv[i], res), e2[i]));
             }
           }
-          __syncwarp();
-          if (has_stats && !straddle) {
-            float t1 = 0.f, t2 = 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) { t1 += S[rr * EPI_LD + lane]; t2 += S2[rr * EPI_LD + lane]; }
-            st[cc * 32 + lane] += t1;
-            st[P.NpA + cc * 32 + lane] += t2;
-          }
+#undef E1_TAKE
         }
         __syncwarp();
       }
@@ -709,7 +777,7 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   P.rps = g.rows_per_sample >= 0x7fffffffLL ? 0x7fffffffu : (uint32_t)(g.rows_per_sample > 0 ? g.rows_per_sample : 1);
   P.lbo_is_k = lbo_is_k & 1;
   P.wait_hint = lbo_is_k >> 1;      // upper bits of the bring-up flag carry the wait hint (C3D_TC_HINT)
-  P.epi_bufs = (g.epi == EPI_SWISH_BWD && g.stats) ? 2 : 1;
+  P.epi_bufs = 1;
   P.dense_contig = (g.a.map == MAP_DENSE && g.a.img_stride == (long long)g.a.OHW * g.a.ld &&
                     (g.a.A2 == nullptr || g.a.img_stride2 == (long long)g.a.OHW * g.a.ld)) ? 1 : 0;
   // TMA feed: rows must be uniformly strided (dense map); the second operand shares the row geometry
