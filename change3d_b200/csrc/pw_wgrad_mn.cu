@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
     }
   } else {
     // ===================== MMA issuer: lane 0 of warp 0 (the epilogue warps have nothing to do until the end) ==========
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      // the whole warp runs the loop (uniform operands stay in uniform registers); lane 0 alone issues
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       // M = 128 (big channels), N = NsP (small channels), K = 8 pixels; both operands MN-major
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NsP >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
@@ -242,22 +244,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         uint64_t dsh = tmpl + (uint64_t)((st + P.off_shi) >> 4), dsl = tmpl + (uint64_t)((st + P.off_slo) >> 4);
         uint64_t dbh = tmpl + (uint64_t)(st >> 4), dbl = tmpl + (uint64_t)((st + P.off_blo) >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_tf32(tmem_base, dbh, dsh, idesc, first);
-          umma_tf32(tmem_base + (uint32_t)P.NsP, dbl, dsh, idesc, first);
-          umma_tf32(tmem_base + (uint32_t)P.NsP, dbh, dsl, idesc, 1u);
+          umma_tf32_if(leader, tmem_base, dbh, dsh, idesc, first);
+          umma_tf32_if(leader, tmem_base + (uint32_t)P.NsP, dbl, dsh, idesc, first);
+          umma_tf32_if(leader, tmem_base + (uint32_t)P.NsP, dbh, dsl, idesc, 1u);
           if (P.nblocks > 1) {
             const uint32_t d2 = tmem_base + (uint32_t)(2 * P.NsP);
-            umma_tf32(d2, dbh + blk16, dsh, idesc, first);
-            umma_tf32(d2 + (uint32_t)P.NsP, dbl + blk16, dsh, idesc, first);
-            umma_tf32(d2 + (uint32_t)P.NsP, dbh + blk16, dsl, idesc, 1u);
+            umma_tf32_if(leader, d2, dbh + blk16, dsh, idesc, first);
+            umma_tf32_if(leader, d2 + (uint32_t)P.NsP, dbl + blk16, dsh, idesc, first);
+            umma_tf32_if(leader, d2 + (uint32_t)P.NsP, dbh + blk16, dsl, idesc, 1u);
           }
           first = 1u;
           dsh += 64; dsl += 64; dbh += 64; dbl += 64;           // next 8 pixels: two 512-byte atoms
         }
-        umma_commit(smem_u32(empty + stage));
+        umma_commit_if(leader, smem_u32(empty + stage));
         if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(done));
+      umma_commit_if(leader, smem_u32(done));
     }
     __syncwarp();
     // ===================== final epilogue: lane = big channel, columns = small channels =====================
