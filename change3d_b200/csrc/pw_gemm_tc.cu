@@ -431,7 +431,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
     // Fused epilogues read a second tensor (E1: y_b for the Swish backward, the residual gradient for the join).
     // Those reads do not depend on the accumulator, so they run one (tile, column chunk) step ahead: the loads of
     // the next step are in flight while this one waits for its MMAs and does its arithmetic.
-    const bool pre_e1 = g.epi != EPI_STORE && g.E1 != nullptr;
+    const bool pre_e1 = (g.epi == EPI_SWISH_BWD || g.epi == EPI_ADD2) && g.E1 != nullptr;
     float4 e1n[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) e1n[i] = f4zero();
@@ -641,6 +641,65 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { E1_TAKE(i, unused_) (void)unused_; }
+          } else if (g.epi == EPI_RELU_ADD || g.epi == EPI_ABSDIFF_BWD) {
+            // Encoder.enhance forward / backward (model/trainer.py:88-108): the output is a frame slice of a larger
+            // tensor (out_img_stride between images), updated in place
+            long long addr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long row = wrow0 + 4 * i + (lane >> 3);
+              addr[i] = -1;
+              if (col_ok && row < g.M) {
+                const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
+                const uint32_t pix = (uint32_t)row - img * (uint32_t)a.OHW;
+                addr[i] = (long long)pix * g.Ns + col + (long long)img * g.out_img_stride;
+              }
+            }
+            if (g.epi == EPI_RELU_ADD) {
+              float4 old[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) old[i] = addr[i] >= 0 ? *reinterpret_cast<const float4*>(g.Y + addr[i]) : f4zero();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (addr[i] >= 0) {
+                  if (g.Y2) st4(g.Y2 + tile_o + (long long)(4 * i) * g.Ns, old[i]);
+                  st4(g.Y + addr[i], f4add(old[i], f4relu(vv[i])));
+                }
+              }
+            } else {
+              // backward of |x0 - x1|: Y (grad of x0) += sign * acc, Y2 (grad of x1) -= sign * acc, in place
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float4 x0[4], x1[4], g0v[4], g1v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = 4 * h + j;
+                  x0[j] = x1[j] = g0v[j] = g1v[j] = f4zero();
+                  if (addr[i] >= 0) {
+                    const long long row = wrow0 + 4 * i + (lane >> 3);
+                    const uint32_t img = (uint32_t)row / (uint32_t)a.OHW;
+                    const long long eaddr = addr[i] - (long long)img * g.out_img_stride + (long long)img * g.e1_img_stride;
+                    x0[j] = ldg4(g.E1 + eaddr); x1[j] = ldg4(g.E2 + eaddr);
+                    g0v[j] = *reinterpret_cast<const float4*>(g.Y + addr[i]);
+                    g1v[j] = *reinterpret_cast<const float4*>(g.Y2 + addr[i]);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = 4 * h + j;
+                  if (addr[i] >= 0) {
+                    const float4 v = vv[i];
+                    float4 t;
+                    t.x = x0[j].x > x1[j].x ? v.x : (x0[j].x < x1[j].x ? -v.x : 0.f);
+                    t.y = x0[j].y > x1[j].y ? v.y : (x0[j].y < x1[j].y ? -v.y : 0.f);
+                    t.z = x0[j].z > x1[j].z ? v.z : (x0[j].z < x1[j].z ? -v.z : 0.f);
+                    t.w = x0[j].w > x1[j].w ? v.w : (x0[j].w < x1[j].w ? -v.w : 0.f);
+                    st4(g.Y + addr[i], f4add(g0v[j], t));
+                    st4(g.Y2 + addr[i], make_float4(g1v[j].x - t.x, g1v[j].y - t.y, g1v[j].z - t.z, g1v[j].w - t.w));
+                  }
+                }
+              }
+            }
           } else {   // EPI_ADD2: residual join (+ the stride-2 shortcut gradient at even pixels)
             float4 e2[8];
 #pragma unroll
@@ -766,8 +825,10 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
 int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, int lbo_is_k, int compact, int use_tma) {
   const GemmArgs& g = g0;
   if (g.a.map != MAP_DENSE && g.a.map != MAP_SUB2) return -1;
-  if (g.epi != EPI_STORE && g.epi != EPI_SWISH_BWD && g.epi != EPI_ADD2) return -1;
-  if (g.out_img_stride != (long long)g.a.OHW * g.Ns) return -1;
+  const bool enhance_epi = g.epi == EPI_RELU_ADD || g.epi == EPI_ABSDIFF_BWD;      // strided, in-place output
+  if (g.epi != EPI_STORE && g.epi != EPI_SWISH_BWD && g.epi != EPI_ADD2 && !enhance_epi) return -1;
+  if (!enhance_epi && g.out_img_stride != (long long)g.a.OHW * g.Ns) return -1;
+  if (enhance_epi && g.stats) return -1;
   if ((g.a.K & 7) || g.a.K < 8 || (g.Ns & 3)) return -1;
   if (g.M >= (1LL << 31) || g.M < tc::BM) return -1;
   if (g.M * (long long)(g.a.ld > g.Ns ? g.a.ld : g.Ns) >= (1LL << 40)) return -1;
