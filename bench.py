@@ -261,8 +261,20 @@ def run_ours(args):
         top = max(families, key=lambda k: families[k]["ms_per_step"])
         peak, peak_src = peaks()
         ach = families[top]["achieved_GBs"]
+        # measured DRAM traffic per launch of this kernel family, from the committed ncu pass (never measured here:
+        # a number taken under a profiler is not a bench value, the traffic of a launch does not depend on timing)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if top in tj.get("families", {}):
+                traffic = tj["families"][top]["dram_bytes_per_launch"]
+                traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        alg_per_launch = int(families[top]["algorithmic_GB_per_step"] * 1e9 / max(1, families[top]["launches_per_step"]))
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
                     "share_of_step": round(families[top]["ms_per_step"] / max(tot_ms, 1e-9), 3),
                     "families": families}
 
