@@ -153,6 +153,11 @@ static int launch_dw_fwd(const float* X, const float* bnp, const float* w, float
 int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, float* Y, double* stats, int N, int T, int IH,
                            int IW, int C, int Cs, cudaStream_t st);      // dw_ring.cu
 
+int c3d_launch_dw_fwd_ring2(const float* X, const float* bnp, const float* w, float* Y, double* stats, int N, int T, int IH,
+                            int IW, int C, int Cs, cudaStream_t st);     // dw_ring.cu (stride 2)
+int c3d_launch_dw_bwd_ring2(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW,
+                            double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st);
+
 extern "C" int c3d_dw_conv_fwd(const float* X, const float* bnp_a, const float* w, float* Y, double* stats, int N,
                                int T, int IH, int IW, int C, int Cs, int stride, void* stream_) {
   if (!X || !bnp_a || !w || !Y || N <= 0 || IH <= 0 || IW <= 0 || C <= 0 || Cs < C || (Cs & 3)) return C3D_ERR_ARG;
@@ -160,6 +165,10 @@ extern "C" int c3d_dw_conv_fwd(const float* X, const float* bnp_a, const float* 
   cudaStream_t st = (cudaStream_t)stream_;
   if (stride == 1 && T >= 3 && T <= 5) {          // row-streaming kernel (each input element read from HBM once)
     const int r = c3d_launch_dw_fwd_ring(X, bnp_a, w, Y, stats, N, T, IH, IW, C, Cs, st);
+    if (r >= 0) return r;
+  }
+  if (stride == 2 && T >= 3 && T <= 5) {
+    const int r = c3d_launch_dw_fwd_ring2(X, bnp_a, w, Y, stats, N, T, IH, IW, C, Cs, st);
     if (r >= 0) return r;
   }
   const int variant = dw_env("C3D_DW_FWD", 0);     // tuning switch: channels/thread x outputs/thread
@@ -422,6 +431,10 @@ extern "C" int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, 
     if (blocks > 148 * 16) blocks = 148 * 16;
     dw_dy_kernel<<<(unsigned)blocks, 256, 0, st>>>(du, y_b, bnp_b, gate, dpool, coef_b, total4, Cs, (long long)T * OH * OW);
     if (cudaGetLastError() != cudaSuccess) return C3D_ERR_CUDA;
+    if (stride == 2) {
+      const int rr = c3d_launch_dw_bwd_ring2(du, y_a, bnp_a, w, dr, dW, stats_a, N, T, IH, IW, C, Cs, st);
+      if (rr >= 0) return rr;
+    }
     if (stride == 1) {          // row-streaming kernel over the pre-computed dy
       const int rr = c3d_launch_dw_bwd_ring(du, y_a, bnp_a, w, dr, dW, stats_a, N, T, IH, IW, C, Cs, st, nullptr, nullptr, nullptr, nullptr, nullptr);
       if (rr >= 0) return rr;

@@ -489,6 +489,361 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// stride (1,2,2): first block of every stage.  Same ring machinery; the forward consumes two input rows per
+// output row (strip = 16 output columns = 33 input columns), the backward produces two input rows per step from
+// two dy rows (strip = 32 input columns = 17 dy columns) — an input pixel only receives the taps whose parity
+// matches: even rows kh = 1, odd rows kh = 0 and 2, same for columns.
+// ------------------------------------------------------------------------------------------------
+struct Geo2 {
+  int N, IH, IW, OH, OW, C, Cs;
+  int nCB, nSEG;
+  int R;
+  long long total_steps, steps_per_cta;
+};
+
+struct Unit2 { int n, cb, sg, r0, r1; };
+
+__device__ __forceinline__ Unit2 decode2(long long step, long long s1, int rows, int nSEG, int nCB) {
+  Unit2 u;
+  const int unit = (int)(step / rows);
+  u.r0 = (int)(step - (long long)unit * rows);
+  const long long left = s1 - step;
+  u.r1 = (long long)(rows - u.r0) < left ? rows : u.r0 + (int)left;
+  u.sg = unit % nSEG;
+  const int t = unit / nSEG;
+  u.cb = t % nCB;
+  u.n = t / nCB;
+  return u;
+}
+
+template <int T>
+__global__ void __launch_bounds__(NT, 2) dw_fwd_ring2_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
+                                                             const float* __restrict__ w, float* __restrict__ Y,
+                                                             double* __restrict__ stats, const Geo2 G) {
+  constexpr int SF = T * TS;
+  extern __shared__ __align__(16) float sm[];
+  float* ring = sm;                                   // [R][T][PIX][CB] input rows
+  float* s_bn = ring + (size_t)G.R * SF;              // [3][CB]
+  double* s_st = reinterpret_cast<double*>(s_bn + 4 * CB);
+  const int tid = threadIdx.x;
+  const int cl = tid & 31, grp = tid >> 5;            // channel, pair of output columns
+  const uint32_t ring_u32 = smem_u32(ring);
+  const long long img_in = (long long)G.IH * G.IW * G.Cs, img_out = (long long)G.OH * G.OW * G.Cs;
+  const long long rowstride = (long long)G.IW * G.Cs;
+
+  Pieces<T> pc;
+  pc.init(tid, G.IH, G.IW, G.Cs);
+
+  const long long s0 = (long long)blockIdx.x * G.steps_per_cta;
+  long long s1 = s0 + G.steps_per_cta;
+  if (s1 > G.total_steps) s1 = G.total_steps;
+
+  long long step = s0;
+  while (step < s1) {
+    const Unit2 u = decode2(step, s1, G.OH, G.nSEG, G.nCB);
+    const int c0 = u.cb * CB, ow0 = u.sg * 16;
+    const int c = c0 + cl;
+    const bool c_ok = c < G.Cs;
+
+    __syncthreads();
+    if (tid < 3 * CB) {
+      const int k = tid >> 5, cc = tid & 31;
+      const int src = k == 0 ? 0 : k == 1 ? 2 : 3;
+      s_bn[tid] = (c0 + cc < G.Cs) ? __ldg(bnp + src * G.Cs + c0 + cc) : 0.f;
+    }
+    if (tid < 2 * CB) s_st[tid] = 0.0;
+    pc.set_unit(tid, 2 * ow0, c0, G.IW, G.Cs);        // ring pixel p <-> input column 2*ow0 - 1 + p
+    float wr[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f;
+    const float* Xu = X + (long long)u.n * T * img_in + (long long)(2 * ow0 - 1) * G.Cs + c0;
+    float* Yt = Y + (long long)u.n * T * img_out + ((long long)u.r0 * G.OW + ow0 + 2 * grp) * G.Cs + c;
+    int nvalid = G.OW - (ow0 + 2 * grp);
+    nvalid = nvalid < 0 ? 0 : nvalid > 2 ? 2 : nvalid;
+    if (!c_ok) nvalid = 0;
+    double st_s = 0.0, st_q = 0.0;
+
+    // input row r lives in slot (r - (2 r0 - 1)) mod R
+    int issue_row = 2 * u.r0 - 1, issue_slot = 0;
+    auto issue_one = [&]() {
+      const bool row_ok = issue_row >= 0 && issue_row < G.IH;
+      const uint32_t dst0 = ring_u32 + (uint32_t)(issue_slot * SF) * 4;
+      const float* src0 = Xu + (long long)issue_row * rowstride;
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.exists >> i & 1) {
+          const bool ok = row_ok && (pc.ok >> i & 1);
+          cp_async16(dst0 + (uint32_t)pc.s_off[i] * 4, ok ? (const void*)(src0 + pc.g_off[i]) : (const void*)X, ok ? 16u : 0u);
+        }
+      }
+      ++issue_row;
+      if (++issue_slot == G.R) issue_slot = 0;
+    };
+    auto transform = [&](int row, int slot) {
+      if (row < 0 || row >= G.IH) return;
+      float* base = ring + (size_t)slot * SF;
+      const int c4 = (tid & 7) * 4;
+      const float4 mean = *reinterpret_cast<const float4*>(s_bn + c4);
+      const float4 scale = *reinterpret_cast<const float4*>(s_bn + CB + c4);
+      const float4 beta = *reinterpret_cast<const float4*>(s_bn + 2 * CB + c4);
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.ok >> i & 1) {
+          float4* p = reinterpret_cast<float4*>(base + pc.s_off[i]);
+          *p = f4relu(f4bn(*p, mean, scale, beta));
+        }
+      }
+    };
+    auto wrap = [&](int x) { return x >= G.R ? x - G.R : x; };
+
+    // group 0 = rows 2r0-1, 2r0, 2r0+1; group k = rows 2(r0+k), 2(r0+k)+1
+    issue_one(); issue_one(); issue_one();
+    cp_async_commit();
+    __syncthreads();                                  // s_bn visible
+    int sl = 0;                                       // slot of row 2*oh - 1
+    for (int oh = u.r0; oh < u.r1; ++oh) {
+      issue_one(); issue_one();
+      cp_async_commit();
+      cp_async_wait<1>();
+      const int sl1 = wrap(sl + 1), sl2 = wrap(sl + 2);
+      if (oh == u.r0) transform(2 * oh - 1, sl);
+      transform(2 * oh, sl1);
+      transform(2 * oh + 1, sl2);
+      __syncthreads();
+      if (nvalid > 0) {
+        const int toff = (4 * grp) * CB + cl;         // output pair (2g, 2g+1) reads ring pixels 4g .. 4g+4
+        const float* b0 = ring + sl * SF + toff;
+        const float* b1 = ring + sl1 * SF + toff;
+        const float* b2 = ring + sl2 * SF + toff;
+        float acc[T][2];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; }
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* rp = (kh == 0 ? b0 : kh == 1 ? b1 : b2) + ti * TS;
+            float in[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) in[j] = rp[j * CB];
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int to = ti - kt + 1;
+              if (to < 0 || to >= T) continue;
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const float wv = wr[kt * 9 + kh * 3 + kw];
+                acc[to][0] = fmaf(wv, in[kw], acc[to][0]);
+                acc[to][1] = fmaf(wv, in[2 + kw], acc[to][1]);
+              }
+            }
+          }
+        }
+        float sf = 0.f, qf = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          float* yp = Yt + (long long)t * img_out;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q < nvalid) {
+              yp[q * G.Cs] = acc[t][q];
+              sf += acc[t][q];
+              qf = fmaf(acc[t][q], acc[t][q], qf);
+            }
+          }
+        }
+        st_s += (double)sf;
+        st_q += (double)qf;
+      }
+      Yt += (long long)G.OW * G.Cs;
+      sl = sl2;
+    }
+    cp_async_wait<0>();
+    if (stats) {
+      if (nvalid > 0) { atomicAdd(&s_st[cl], st_s); atomicAdd(&s_st[CB + cl], st_q); }
+      __syncthreads();
+      if (tid < 2 * CB) {
+        const int k = tid >> 5, cc = tid & 31;
+        if (c0 + cc < G.Cs) atomicAdd(stats + ((long long)u.n * 2 + k) * G.Cs + c0 + cc, s_st[tid]);
+      }
+    }
+    step += u.r1 - u.r0;
+  }
+}
+
+// backward, stride 2: step m produces input rows 2m, 2m+1 of a 32-column strip from dy rows m, m+1
+template <int T>
+__global__ void __launch_bounds__(NT, 1) dw_bwd_ring2_kernel(const float* __restrict__ DY, const float* __restrict__ YA,
+                                                             const float* __restrict__ bnp_a, const float* __restrict__ w,
+                                                             float* __restrict__ DR, float* __restrict__ dW,
+                                                             double* __restrict__ stats_a, const Geo2 G) {
+  constexpr int SF = T * TS;
+  extern __shared__ __align__(16) float sm[];
+  float* ring = sm;                                                  // [R][T][PIX][CB] dy rows
+  float* s_dw = ring + (size_t)G.R * SF;                             // [27][CB]
+  double* s_st = reinterpret_cast<double*>(s_dw + 28 * CB);          // [2][CB]
+  const int tid = threadIdx.x;
+  const int cl = tid & 31, grp = tid >> 5;                           // channel, group of 4 input columns
+  const uint32_t ring_u32 = smem_u32(ring);
+  const long long img_in = (long long)G.IH * G.IW * G.Cs, img_out = (long long)G.OH * G.OW * G.Cs;
+  const long long rowstride_o = (long long)G.OW * G.Cs, rowstride_i = (long long)G.IW * G.Cs;
+  const int nsteps = (G.IH + 1) >> 1;                                // input row pairs
+
+  Pieces<T> pc;
+  pc.init(tid, G.OH, G.OW, G.Cs);
+
+  const long long s0 = (long long)blockIdx.x * G.steps_per_cta;
+  long long s1 = s0 + G.steps_per_cta;
+  if (s1 > G.total_steps) s1 = G.total_steps;
+
+  long long step = s0;
+  while (step < s1) {
+    const Unit2 u = decode2(step, s1, nsteps, G.nSEG, G.nCB);
+    const int c0 = u.cb * CB, iw0 = u.sg * SEGW, oc0 = iw0 >> 1;      // first dy column of the strip
+    const int c = c0 + cl;
+    const bool c_ok = c < G.Cs;
+
+    __syncthreads();
+    for (int i = tid; i < 27 * CB; i += NT) s_dw[i] = 0.f;
+    if (tid < 2 * CB) s_st[tid] = 0.0;
+    pc.set_unit(tid, oc0 + 1, c0, G.OW, G.Cs);                       // ring pixel p <-> dy column oc0 + p
+    float wr[27], dwacc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) { wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f; dwacc[t] = 0.f; }
+    float mean_a = 0.f, rstd_a = 0.f, scale_a = 0.f, beta_a = 0.f;
+    if (c_ok) {
+      mean_a = __ldg(bnp_a + c); rstd_a = __ldg(bnp_a + G.Cs + c);
+      scale_a = __ldg(bnp_a + 2 * G.Cs + c); beta_a = __ldg(bnp_a + 3 * G.Cs + c);
+    }
+    const float* DYu = DY + (long long)u.n * T * img_out + (long long)oc0 * G.Cs + c0;
+    const long long toff_g = (long long)u.n * T * img_in + ((long long)(2 * u.r0) * G.IW + iw0 + 4 * grp) * G.Cs + c;
+    const float* YAt = YA + toff_g;                                  // frame 0, input row 2*r0
+    float* DRt = DR + toff_g;
+    int nvalid = G.IW - (iw0 + 4 * grp);
+    nvalid = nvalid < 0 ? 0 : nvalid > 4 ? 4 : nvalid;
+    if (!c_ok) nvalid = 0;
+    double st_s = 0.0, st_t = 0.0;
+
+    // dy row r lives in slot (r - r0) mod R
+    int issue_row = u.r0, issue_slot = 0;
+    auto issue = [&]() {
+      const bool row_ok = issue_row >= 0 && issue_row < G.OH;
+      const uint32_t dst0 = ring_u32 + (uint32_t)(issue_slot * SF) * 4;
+      const float* src0 = DYu + (long long)issue_row * rowstride_o;
+#pragma unroll
+      for (int i = 0; i < Pieces<T>::NE; ++i) {
+        if (pc.exists >> i & 1) {
+          const bool ok = row_ok && (pc.ok >> i & 1);
+          cp_async16(dst0 + (uint32_t)pc.s_off[i] * 4, ok ? (const void*)(src0 + pc.g_off[i]) : (const void*)DY, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      ++issue_row;
+      if (++issue_slot == G.R) issue_slot = 0;
+    };
+
+    issue(); issue(); issue();                        // rows r0, r0+1, r0+2
+    int sl = 0;                                       // slot of dy row m
+    for (int m = u.r0; m < u.r1; ++m) {
+      issue();                                        // row m + 3
+      const int nrows = (2 * m + 1 < G.IH) ? 2 : 1;   // odd image height: the last pair has one row
+      float ya[T][2][4];
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            ya[t][e][x] = (x < nvalid && e < nrows) ? __ldg(YAt + (long long)t * img_in + (long long)e * rowstride_i + x * G.Cs) : 0.f;
+      cp_async_wait<2>();                             // rows m, m + 1 have landed
+      const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
+      __syncthreads();
+      if (nvalid > 0) {
+        const int toff = (2 * grp) * CB + cl;          // dy columns oc0 + 2g .. oc0 + 2g + 2
+        const float* b0 = ring + sl * SF + toff;       // dy row m
+        const float* b1 = ring + sl1 * SF + toff;      // dy row m + 1
+        float a[T][2][4], da[T][2][4];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              a[t][e][x] = (x < nvalid && e < nrows) ? fmaxf(fmaf(ya[t][e][x] - mean_a, scale_a, beta_a), 0.f) : 0.f;
+              da[t][e][x] = 0.f;
+            }
+#pragma unroll
+        for (int to = 0; to < T; ++to) {
+          float d0[3], d1[3];                          // dy rows m / m + 1 at columns h, h + 1, h + 2
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { d0[j] = b0[to * TS + j * CB]; d1[j] = b1[to * TS + j * CB]; }
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            const int ti = to + kt - 1;
+            if (ti < 0 || ti >= T) continue;
+            // (input row e, kh, dy row): (0, 1, m), (1, 0, m + 1), (1, 2, m)
+            // (input col x, kw, dy col j): (0,1,0) (1,0,1) (1,2,0) (2,1,1) (3,0,2) (3,2,1)
+#define DW2_TAP(e, kh, dv, x, kw, j)                                             \
+            {                                                                    \
+              const int tap = kt * 9 + (kh) * 3 + (kw);                          \
+              da[ti][e][x] = fmaf(wr[tap], dv[j], da[ti][e][x]);                 \
+              dwacc[tap] = fmaf(a[ti][e][x], dv[j], dwacc[tap]);                 \
+            }
+#define DW2_ROW(e, kh, dv)                                                       \
+            DW2_TAP(e, kh, dv, 0, 1, 0) DW2_TAP(e, kh, dv, 1, 0, 1) DW2_TAP(e, kh, dv, 1, 2, 0) \
+            DW2_TAP(e, kh, dv, 2, 1, 1) DW2_TAP(e, kh, dv, 3, 0, 2) DW2_TAP(e, kh, dv, 3, 2, 1)
+            DW2_ROW(0, 1, d0)
+            DW2_ROW(1, 0, d1)
+            DW2_ROW(1, 2, d0)
+#undef DW2_ROW
+#undef DW2_TAP
+          }
+        }
+        float sf = 0.f, tf = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (e >= nrows) continue;
+            float* dp = DRt + (long long)t * img_in + (long long)e * rowstride_i;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              if (x < nvalid) {
+                const float v = a[t][e][x] > 0.f ? da[t][e][x] : 0.f;
+                dp[x * G.Cs] = v;
+                sf += v;
+                tf = fmaf(v, (ya[t][e][x] - mean_a) * rstd_a, tf);
+              }
+            }
+          }
+        st_s += (double)sf;
+        st_t += (double)tf;
+      }
+      YAt += 2 * rowstride_i;
+      DRt += 2 * rowstride_i;
+      sl = sl1;
+    }
+    cp_async_wait<0>();
+    if (nvalid > 0) {
+#pragma unroll
+      for (int t = 0; t < 27; ++t) atomicAdd(&s_dw[t * CB + cl], dwacc[t]);
+      atomicAdd(&s_st[cl], st_s);
+      atomicAdd(&s_st[CB + cl], st_t);
+    }
+    __syncthreads();
+    for (int i = tid; i < 27 * CB; i += NT) {
+      const int t = i >> 5, cc = i & 31;
+      if (c0 + cc < G.C) atomicAdd(dW + (c0 + cc) * 27 + t, s_dw[i]);
+    }
+    if (tid < 2 * CB) {
+      const int k = tid >> 5, cc = tid & 31;
+      if (c0 + cc < G.Cs) atomicAdd(stats_a + (long long)k * G.Cs + c0 + cc, s_st[tid]);
+    }
+    step += u.r1 - u.r0;
+  }
+}
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -588,4 +943,65 @@ int c3d_launch_dw_bwd_ring(const float* dy, const float* ya, const float* bnp_a,
     case 4: return launch_bwd<4>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
     default: return launch_bwd<5>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
   }
+}
+
+// ---- stride-2 launchers (first block of each stage).  Return -1 when the shape is not handled here. ----
+static bool plan2(dwr::Geo2& G, int T, int N, int IH, int IW, int C, int Cs, int R, int rows, int nseg, size_t extra, size_t& smem,
+                  int& grid, int ctas_per_sm) {
+  if (IW < 1 || IH < 1 || (Cs & 3) || T < 3 || T > 5) return false;
+  if ((long long)T * IH * IW * Cs >= (1LL << 31)) return false;
+  G.N = N; G.IH = IH; G.IW = IW; G.OH = (IH - 1) / 2 + 1; G.OW = (IW - 1) / 2 + 1; G.C = C; G.Cs = Cs;
+  G.nCB = (Cs + dwr::CB - 1) / dwr::CB;
+  G.nSEG = nseg;
+  G.R = R;
+  int dev = 0, sms = 148, max_smem = 227 * 1024;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  smem = (size_t)R * T * dwr::TS * 4 + extra;
+  if (smem > (size_t)max_smem) return false;
+  if (ctas_per_sm == 2 && 2 * (smem + 1024) > (size_t)max_smem + 1024) ctas_per_sm = 1;
+  G.total_steps = (long long)N * G.nCB * nseg * rows;
+  long long g = (long long)sms * ctas_per_sm;
+  if (g > G.total_steps) g = G.total_steps;
+  G.steps_per_cta = (G.total_steps + g - 1) / g;
+  grid = (int)((G.total_steps + G.steps_per_cta - 1) / G.steps_per_cta);
+  return true;
+}
+
+int c3d_launch_dw_fwd_ring2(const float* X, const float* bnp, const float* w, float* Y, double* stats, int N, int T, int IH,
+                            int IW, int C, int Cs, cudaStream_t st) {
+  if (!dwr::env_int("C3D_DW_RING", 1) || !dwr::env_int("C3D_DW_RING2", 1)) return -1;
+  dwr::Geo2 G;
+  size_t smem = 0;
+  int grid = 0;
+  const int OH = (IH - 1) / 2 + 1, OW = (IW - 1) / 2 + 1;
+  const size_t extra = (size_t)(4 * dwr::CB * 4 + 2 * dwr::CB * 8);
+  if (!plan2(G, T, N, IH, IW, C, Cs, 7, OH, (OW + 15) / 16, extra, smem, grid, 2)) return -1;
+  cudaError_t e;
+#define C3D_LAUNCH_FWD2(TT)                                                                                                 \
+  e = cudaFuncSetAttribute(dwr::dw_fwd_ring2_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+  if (e != cudaSuccess) return C3D_ERR_SMEM;                                                                                 \
+  dwr::dw_fwd_ring2_kernel<TT><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+  if (T == 3) { C3D_LAUNCH_FWD2(3) } else if (T == 4) { C3D_LAUNCH_FWD2(4) } else { C3D_LAUNCH_FWD2(5) }
+#undef C3D_LAUNCH_FWD2
+  return c3d_check_last(cudaGetLastError());
+}
+
+int c3d_launch_dw_bwd_ring2(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW,
+                            double* stats_a, int N, int T, int IH, int IW, int C, int Cs, cudaStream_t st) {
+  if (!dwr::env_int("C3D_DW_RING", 1) || !dwr::env_int("C3D_DW_RING2", 1)) return -1;
+  dwr::Geo2 G;
+  size_t smem = 0;
+  int grid = 0;
+  const size_t extra = (size_t)(28 * dwr::CB * 4 + 2 * dwr::CB * 8);
+  if (!plan2(G, T, N, IH, IW, C, Cs, 5, (IH + 1) / 2, (IW + dwr::SEGW - 1) / dwr::SEGW, extra, smem, grid, 1)) return -1;
+  cudaError_t e;
+#define C3D_LAUNCH_BWD2(TT)                                                                                                 \
+  e = cudaFuncSetAttribute(dwr::dw_bwd_ring2_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+  if (e != cudaSuccess) return C3D_ERR_SMEM;                                                                                 \
+  dwr::dw_bwd_ring2_kernel<TT><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
+  if (T == 3) { C3D_LAUNCH_BWD2(3) } else if (T == 4) { C3D_LAUNCH_BWD2(4) } else { C3D_LAUNCH_BWD2(5) }
+#undef C3D_LAUNCH_BWD2
+  return c3d_check_last(cudaGetLastError());
 }

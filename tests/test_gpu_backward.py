@@ -41,7 +41,8 @@ def test_pw_wgrad(n, k, M):
 
 @pytest.mark.parametrize("T,stride,C,H,W,N,se", [(3, 1, 216, 7, 32, 3, True), (3, 1, 108, 40, 64, 2, False), (3, 1, 54, 70, 128, 2, True),
                                                  (5, 1, 108, 9, 32, 2, True), (4, 1, 432, 6, 16, 2, False), (3, 1, 54, 6, 9, 1, True),
-                                                 (3, 2, 54, 16, 12, 2, True), (3, 1, 54, 12, 20, 2, False)])
+                                                 (3, 2, 54, 16, 12, 2, True), (3, 1, 54, 12, 20, 2, False),
+                                                 (3, 2, 54, 40, 128, 2, True), (3, 2, 108, 22, 64, 3, False), (4, 2, 216, 12, 34, 2, True)])
 def test_dw_conv_backward(T, stride, C, H, W, N, se):
     """conv_b backward through the C ABI (BN_b / SE backward transform of du, transposed depthwise conv, ReLU mask of
     BN_a, depthwise weight gradient, BN_a backward sums) against fp64 autograd of the same formulas

@@ -56,7 +56,9 @@ def test_pw_gemm_forward_with_stats(cin, cout, M):
                                               # blocks of 32 / 16 / 8, swizzled ring), enough rows that a CTA's span crosses
                                               # (sample, channel block) segments; odd width -> generic kernel
                                               (3, 1, 216, 7, 32, 3), (3, 1, 108, 40, 64, 2), (3, 1, 54, 70, 128, 2),
-                                              (5, 1, 108, 9, 32, 2), (4, 1, 432, 6, 16, 2), (3, 1, 54, 6, 9, 1)])
+                                              (5, 1, 108, 9, 32, 2), (4, 1, 432, 6, 16, 2), (3, 1, 54, 6, 9, 1),
+                                              # stride-2 ring kernel: strips of 16 output columns, spans crossing units, odd sizes
+                                              (3, 2, 54, 40, 128, 2), (3, 2, 108, 22, 64, 3), (4, 2, 216, 11, 34, 2), (3, 2, 24, 256, 64, 1)])
 def test_dw_conv_forward(T, stride, C, H, W, N):
     ops = _ops()
     g = torch.Generator().manual_seed(T * 100 + C)
