@@ -61,6 +61,8 @@ SIGNATURES = {
                                _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp],
     "c3d_dw_conv_bwd": [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _fp],
     "c3d_colsum": [_fp, _ll, _i, _fp, _fp],
+    "c3d_convt_col2im": [_fp, _fp, _ll, _fp, _fp, _i, _i, _i, _i, _fp],
+    "c3d_convt_im2col": [_fp, _fp, _i, _i, _i, _i, _fp],
     "c3d_stem_bwd": [C.POINTER(_fp), C.POINTER(_ll), C.POINTER(_ll), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                      _i, _i, _i, _i, _fp],
     "c3d_dec_head_bwd": [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _fp],

@@ -1,6 +1,10 @@
 // ChangeDecoder head (model/change_decoder.py:53-55,76-79): Conv2d 3x3 (C -> ncls, pad 1, no bias)
 // [+ sigmoid], NHWC in, NCHW out (the layout the reference returns), and its backward.
-// The 1x1 Conv2d + ConvTranspose2d up-blocks run through the pointwise-GEMM family (pw_gemm.cu).
+// The 1x1 Conv2d of the up-blocks runs through the pointwise-GEMM family.  ConvTranspose2d(k4, s2, p1)
+// (model/change_decoder.py:30-45) is split into a dense GEMM over the input grid that produces all 16 kernel
+// positions per input pixel, U[j][i][ky][kx][co] = sum_ci t[j][i][ci] W[ci][co][ky][kx], and the col2im gather
+// below (output pixel (y, x) sums the 4 positions with 2j-1+ky = y, 2i-1+kx = x, plus bias and the skip tensor);
+// the backward uses the mirrored im2col so that d t and d W are dense GEMMs as well (tcgen05 kernels).
 #include "c3d_common.cuh"
 #include "../../include/change3d_b200.h"
 
@@ -178,5 +182,75 @@ extern "C" int c3d_dec_head_bwd(const float* dpred, const float* pred, const flo
   const int ntiles = ((W + 31) / 32) * ((H + 7) / 8) * B;
   int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
   dec_head_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(dpred, pred, X, w, dX, dW, B, H, W, C, ncls, is_sigmoid);
+  return c3d_check_last(cudaGetLastError());
+}
+
+
+// ---------------- ConvTranspose2d(k4, s2, p1) as dense GEMM + col2im / im2col ----------------
+// out[b][y][x][co] = bias[co] + skip[b][y][x][co] + sum_{ky == (y+1) mod 2 (+2)} sum_{kx} U[b][(y+1-ky)/2][(x+1-kx)/2][ky][kx][co]
+__global__ void __launch_bounds__(256) convt_col2im_kernel(const float* __restrict__ U, const float* __restrict__ skip,
+                                                           long long skip_img_stride, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int h, int w, int cout, long long total4) {
+  const int c4n = cout >> 2, OW = 2 * w, OH = 2 * h;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    long long pix = idx / c4n;
+    const int x = (int)(pix % OW);
+    pix /= OW;
+    const int y = (int)(pix % OH);
+    const int b = (int)(pix / OH);
+    float4 acc = ldg4(bias + c);
+    if (skip) acc = f4add(acc, ldg4(skip + (long long)b * skip_img_stride + ((long long)y * OW + x) * cout + c));
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int ky = ((y + 1) & 1) + 2 * a, j = (y + 1 - ky) >> 1;
+      if (y + 1 - ky < 0 || j >= h) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kx = ((x + 1) & 1) + 2 * e, i = (x + 1 - kx) >> 1;
+        if (x + 1 - kx < 0 || i >= w) continue;
+        acc = f4add(acc, ldg4(U + ((((long long)b * h + j) * w + i) * 16 + ky * 4 + kx) * cout + c));
+      }
+    }
+    st4(out + (((long long)b * OH + y) * OW + x) * cout + c, acc);
+  }
+}
+
+// V[b][j][i][ky][kx][co] = d_out[b][2j-1+ky][2i-1+kx][co]  (zero outside the image)
+__global__ void __launch_bounds__(256) convt_im2col_kernel(const float* __restrict__ dout, float* __restrict__ V, int h, int w,
+                                                           int cout, long long total4) {
+  const int c4n = cout >> 2, OW = 2 * w, OH = 2 * h;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    long long r = idx / c4n;
+    const int tap = (int)(r & 15);
+    r >>= 4;
+    const int i = (int)(r % w);
+    r /= w;
+    const int j = (int)(r % h);
+    const int b = (int)(r / h);
+    const int y = 2 * j - 1 + (tap >> 2), x = 2 * i - 1 + (tap & 3);
+    float4 v = f4zero();
+    if (y >= 0 && y < OH && x >= 0 && x < OW) v = ldg4(dout + (((long long)b * OH + y) * OW + x) * cout + c);
+    st4(V + idx * 4, v);
+  }
+}
+
+extern "C" int c3d_convt_col2im(const float* U, const float* skip, long long skip_img_stride, const float* bias, float* out,
+                                int B, int h, int w, int cout, void* stream_) {
+  if (!U || !bias || !out || B <= 0 || h <= 0 || w <= 0 || cout <= 0 || (cout & 3)) return C3D_ERR_ARG;
+  const long long total4 = (long long)B * 4 * h * w * (cout >> 2);
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  convt_col2im_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(U, skip, skip_img_stride, bias, out, h, w, cout, total4);
+  return c3d_check_last(cudaGetLastError());
+}
+
+extern "C" int c3d_convt_im2col(const float* dout, float* V, int B, int h, int w, int cout, void* stream_) {
+  if (!dout || !V || B <= 0 || h <= 0 || w <= 0 || cout <= 0 || (cout & 3)) return C3D_ERR_ARG;
+  const long long total4 = (long long)B * h * w * 16 * (cout >> 2);
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  convt_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(dout, V, h, w, cout, total4);
   return c3d_check_last(cudaGetLastError());
 }

@@ -830,7 +830,7 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   if (!enhance_epi && g.out_img_stride != (long long)g.a.OHW * g.Ns) return -1;
   if (enhance_epi && g.stats) return -1;
   if ((g.a.K & 7) || g.a.K < 8 || (g.Ns & 3)) return -1;
-  if (g.M >= (1LL << 31) || g.M < tc::BM) return -1;
+  if (g.M >= (1LL << 31) || g.M < 1) return -1;      // a single partial tile is fine: TMA zero-fills, the epilogue masks
   if (g.M * (long long)(g.a.ld > g.Ns ? g.a.ld : g.Ns) >= (1LL << 40)) return -1;
   tc::Params P;
   P.g = g;

@@ -244,14 +244,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         uint64_t dsh = tmpl + (uint64_t)((st + P.off_shi) >> 4), dsl = tmpl + (uint64_t)((st + P.off_slo) >> 4);
         uint64_t dbh = tmpl + (uint64_t)(st >> 4), dbl = tmpl + (uint64_t)((st + P.off_blo) >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_tf32_if(leader, tmem_base, dbh, dsh, idesc, first);
-          umma_tf32_if(leader, tmem_base + (uint32_t)P.NsP, dbl, dsh, idesc, first);
-          umma_tf32_if(leader, tmem_base + (uint32_t)P.NsP, dbh, dsl, idesc, 1u);
-          if (P.nblocks > 1) {
-            const uint32_t d2 = tmem_base + (uint32_t)(2 * P.NsP);
-            umma_tf32_if(leader, d2, dbh + blk16, dsh, idesc, first);
-            umma_tf32_if(leader, d2 + (uint32_t)P.NsP, dbl + blk16, dsh, idesc, first);
-            umma_tf32_if(leader, d2 + (uint32_t)P.NsP, dbh + blk16, dsl, idesc, 1u);
+          for (int b = 0; b < P.nblocks; ++b) {
+            const uint32_t db = tmem_base + (uint32_t)(b * 2 * P.NsP);
+            const uint64_t bo = (uint64_t)((uint32_t)b * blk16);
+            umma_tf32_if(leader, db, dbh + bo, dsh, idesc, first);
+            umma_tf32_if(leader, db + (uint32_t)P.NsP, dbl + bo, dsh, idesc, first);
+            umma_tf32_if(leader, db + (uint32_t)P.NsP, dbh + bo, dsl, idesc, 1u);
           }
           first = 1u;
           dsh += 64; dsl += 64; dbh += 64; dbl += 64;           // next 8 pixels: two 512-byte atoms
@@ -348,7 +346,7 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   P.Gs = (P.small.K + 31) / 32;
   P.nblocks = (P.Gb + 3) / 4;
   P.NsP = P.Gs * 32;
-  if (P.NsP > 256 || P.nblocks > 2) return -1;
+  if (P.NsP > 256 || P.nblocks > 4) return -1;
   int cols = 32;
   while (cols < P.nblocks * 2 * P.NsP) cols <<= 1;
   if (cols > 512) return -1;

@@ -206,21 +206,24 @@ def feature_view(f: torch.Tensor):
     return g, H * W * Cc
 
 
-def decoder_up_forward(up, c_hi, hi_stride: int, h: int, w: int, skip, skip_stride: int, pack_idx: torch.Tensor):
-    """One up block: skip + ConvTranspose2d(k4,s2,p1)(Conv2d1x1(c_hi)) -> dense (B,2h,2w,Cout)."""
+def decoder_up_forward(up, c_hi, hi_stride: int, h: int, w: int, skip, skip_stride: int, pack_idx: torch.Tensor = None):
+    """One up block: skip + ConvTranspose2d(k4,s2,p1)(Conv2d1x1(c_hi)) -> dense (B,2h,2w,Cout).
+    The transposed conv is a dense GEMM t x W_all (all 16 kernel positions per input pixel) + a col2im gather."""
     conv1, convt = up[0], up[1]
     cmid, chi = conv1.weight.shape[0], conv1.weight.shape[1]
     cout = convt.weight.shape[1]
     B = c_hi.shape[0]
     dev = conv1.weight.device
+    M = B * h * w
     t = torch.empty(B, h, w, cmid, device=dev, dtype=torch.float32)
     ops.pw_gemm(ops.operand(c_hi, ld=chi, OH=h, OW=w, img_stride=hi_stride), conv1.weight, w_sr=1, w_so=chi,
-                Kred=chi, N=cmid, Ns=cmid, M=B * h * w, Y=t)
-    packed = convt.weight.detach().reshape(-1)[pack_idx]
+                Kred=chi, N=cmid, Ns=cmid, M=M, Y=t)
+    w_all = convt.weight.detach().permute(0, 2, 3, 1).reshape(cmid, 16 * cout).contiguous()   # [ci][(ky,kx,co)]
+    U = torch.empty(M, 16 * cout, device=dev, dtype=torch.float32)
+    ops.pw_gemm(ops.operand(t, ld=cmid, OH=h, OW=w), w_all, w_sr=16 * cout, w_so=1, Kred=cmid, N=16 * cout,
+                Ns=16 * cout, M=M, Y=U)
     out = torch.empty(B, 2 * h, 2 * w, cout, device=dev, dtype=torch.float32)
-    ops.pw_gemm(ops.operand(t, ld=cmid, OH=h, OW=w, map_=MAP_CONVT_FWD), packed, w_sr=cout, w_so=1,
-                w_cls_stride=4 * cmid * cout, Kred=4 * cmid, N=cout, Ns=cout, M=B * h * w, Y=out,
-                out_img_stride=4 * h * w * cout, epi=EPI_CONVT, bias=convt.bias, E1=skip, e1_img_stride=skip_stride)
+    ops.convt_col2im(U, skip, skip_stride, convt.bias, out, B, h, w, cout)
     return out, t
 
 
@@ -436,20 +439,16 @@ def decoder_up_backward(up, d_out, t, c_hi, hi_stride: int, h: int, w: int, ga: 
     M = B * h * w
     g_w1, g_wt, g_bias = ga.next(), ga.next(), ga.next()
     ops.colsum(d_out, g_bias)
-    # d t = sum over the 16 taps of d_out gathered at (2j-1+ky, 2i-1+kx): four accumulating GEMMs (one per ky)
-    packed = convt.weight.detach().permute(2, 3, 1, 0).reshape(16 * cout, cmid).contiguous()   # [(ky,kx,co)][ci]
+    # V[(j,i)][(ky,kx,co)] = d_out[2j-1+ky][2i-1+kx][co]; then d t = V x W_all^T and d W_all = t^T x V are dense
+    V = torch.empty(M, 16 * cout, device=dev, dtype=torch.float32)
+    ops.convt_im2col(d_out, V, B, h, w, cout)
+    w_all = convt.weight.detach().permute(0, 2, 3, 1).reshape(cmid, 16 * cout).contiguous()   # [ci][(ky,kx,co)]
     d_t = torch.empty(B, h, w, cmid, device=dev, dtype=torch.float32)
-    for ky in range(4):
-        gath = ops.operand(d_out, ld=cout, OH=h, OW=w, IH=2 * h, IW=2 * w, img_stride=4 * h * w * cout,
-                           map_=MAP_CONVT_BWD, seg0=4 * ky, nseg=4)
-        ops.pw_gemm(gath, packed[4 * ky * cout:], w_sr=cmid, w_so=1, Kred=4 * cout, N=cmid, Ns=cmid, M=M, Y=d_t,
-                    epi=EPI_STORE if ky == 0 else EPI_ADD2, E1=None if ky == 0 else d_t)
-    # dWt[ci][co][ky][kx] = sum t[j,i,ci] * d_out[2j-1+ky, 2i-1+kx, co]
+    ops.pw_gemm(ops.operand(V, ld=16 * cout, OH=h, OW=w), w_all, w_sr=1, w_so=16 * cout, Kred=16 * cout, N=cmid,
+                Ns=cmid, M=M, Y=d_t)
     dWp = torch.zeros(cmid, 16 * cout, device=dev, dtype=torch.float32)
-    gath_all = ops.operand(d_out, ld=cout, OH=h, OW=w, IH=2 * h, IW=2 * w, img_stride=4 * h * w * cout,
-                           map_=MAP_CONVT_BWD)
-    ops.pw_wgrad(ops.operand(t, ld=cmid, OH=h, OW=w), gath_all, M=M, dW=dWp, dw_sn=16 * cout, dw_sk=1, N=cmid,
-                 K=16 * cout)
+    ops.pw_wgrad(ops.operand(t, ld=cmid, OH=h, OW=w), ops.operand(V, ld=16 * cout, OH=h, OW=w), M=M, dW=dWp,
+                 dw_sn=16 * cout, dw_sk=1, N=cmid, K=16 * cout)
     g_wt.copy_(dWp.view(cmid, 4, 4, cout).permute(0, 3, 1, 2))
     # 1x1 conv backward
     d_chi = torch.empty(B, h, w, chi, device=dev, dtype=torch.float32)

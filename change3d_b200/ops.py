@@ -249,6 +249,18 @@ def colsum(X: torch.Tensor, out: torch.Tensor) -> None:
     L.check(L.load().c3d_colsum(_ptr(X), X.numel() // Cs, Cs, _ptr(out), _stream()), "c3d_colsum")
 
 
+def convt_col2im(U: torch.Tensor, skip, skip_img_stride: int, bias: torch.Tensor, out: torch.Tensor, B: int, h: int,
+                 w: int, cout: int) -> None:
+    with _Timed("convt_col2im", 4 * (U.numel() + 2 * out.numel())):
+        L.check(L.load().c3d_convt_col2im(_ptr(U), _ptr(skip), skip_img_stride, _ptr(bias), _ptr(out), B, h, w, cout,
+                                          _stream()), "c3d_convt_col2im")
+
+
+def convt_im2col(d_out: torch.Tensor, V: torch.Tensor, B: int, h: int, w: int, cout: int) -> None:
+    with _Timed("convt_im2col", 4 * (d_out.numel() + V.numel())):
+        L.check(L.load().c3d_convt_im2col(_ptr(d_out), _ptr(V), B, h, w, cout, _stream()), "c3d_convt_im2col")
+
+
 def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc) -> None:
     T = len(frames)
     B, _, H, W, _ = y.shape

@@ -183,6 +183,17 @@ int c3d_stem_bwd(const float* const* frame_ptr, const long long* stride_n, const
 int c3d_dec_head_bwd(const float* dpred, const float* pred, const float* X, const float* w, float* dX, float* dW,
                      int B, int H, int W, int C, int ncls, int is_sigmoid, void* cuda_stream);
 
+/* ConvTranspose2d(k=4, s=2, p=1) of the decoder up-blocks (model/change_decoder.py:30-45,71-73) split into a dense
+ * GEMM and a gather: U = t x W with U[b][j][i][ky][kx][co] (c3d_pw_gemm, N = 16*cout), then
+ * out[b][y][x][co] = bias[co] + skip[b][y][x][co] + the 4 entries of U with 2j-1+ky = y, 2i-1+kx = x.
+ * skip may be NULL; skip_img_stride = elements between images of skip.  out is dense (B, 2h, 2w, cout). */
+int c3d_convt_col2im(const float* U, const float* skip, long long skip_img_stride, const float* bias, float* out,
+                     int B, int h, int w, int cout, void* cuda_stream);
+
+/* Its mirror for the backward: V[b][j][i][ky][kx][co] = d_out[b][2j-1+ky][2i-1+kx][co] (zero outside), so that
+ * d t = V x W^T and d W = t^T x V are dense (c3d_pw_gemm / c3d_pw_wgrad). */
+int c3d_convt_im2col(const float* d_out, float* V, int B, int h, int w, int cout, void* cuda_stream);
+
 /* torch.optim.Adam step (scripts/train_BCD.py:284-290: L2 weight decay added to the gradient) on flat, 16-byte
  * aligned fp32 buffers; g is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
 int c3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
