@@ -10,8 +10,8 @@
 //            buffer, the prologue's second tensor (y for the BN backward, the ReLU pre-activation) in the lo buffer
 //   MMA    = M 128 (a block of 4 channel groups of the wider operand) x N (the narrower operand) x K 8 pixels, three
 //            terms of the 3xTF32 split into two TMEM accumulators (main + correction) that live for the whole CTA
-//   warps  = 0-3 final epilogue (TMEM -> fp32 atomics; lane 0 of warp 0 issues the MMAs until then), 4 TMA issuer,
-//            5-15 producers (all of them work on every stage, one (operand, channel group) job at a time)
+//   warps  = 0-3 final epilogue (TMEM -> fp32 atomics; until then warp 0 issues the MMAs and warp 1 the TMA copies),
+//            4-15 producers (all of them work on every stage, one (operand, channel group, 16 rows) job at a time)
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -21,8 +21,8 @@ namespace tcm {
 
 using namespace tc;
 
-constexpr int NPW = 11;                    // producer warps
-constexpr int NTHREADS = (5 + NPW) * 32;   // 16 warps: 128 registers per thread
+constexpr int NPW = 12;                    // producer warps
+constexpr int NTHREADS = (4 + NPW) * 32;   // 16 warps: 128 registers per thread
 constexpr int MAX_STAGES = 6;
 
 struct Params {
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
   const bool big2 = (P.big.mode == PRO_BNBWD || P.big.mode == PRO_ABSDIFF || P.big.mode == PRO_MASK_POS);
   const bool small2 = (P.small.mode == PRO_BNBWD || P.small.mode == PRO_ABSDIFF || P.small.mode == PRO_MASK_POS);
 
-  if (warp >= 5) {
+  if (warp >= 4) {
     // ===================== producers: in-place prologue + split of (operand, channel group) jobs ====================
-    const int pw = warp - 5;
+    const int pw = warp - 4;
     const int nrc = P.PT / 16;                       // 16-row chunks per channel group
     const int njobs = (P.Gb + P.Gs) * nrc;
     int stage = 0;
@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       if (lane == 0) mbar_arrive(smem_u32(full + stage));
       if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 4) {
-    // ===================== TMA issuer =====================
+  } else {
+    // ===================== TMA issuer: epilogue warp 1 (idle until the end) =====================
+    if (warp == 1) {
     const uint32_t bytes = (uint32_t)P.PT * 128u * (uint32_t)(P.Gb * (big2 ? 2 : 1) + P.Gs * (small2 ? 2 : 1));
     int stage = 0;
     uint32_t phase = 0;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       __syncwarp();
       if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
     }
-  } else {
+    }
     // ===================== MMA issuer: lane 0 of warp 0 (the epilogue warps have nothing to do until the end) ==========
     if (warp == 0) {
       // the whole warp runs the loop (uniform operands stay in uniform registers); lane 0 alone issues
@@ -399,7 +400,7 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
             P.big.mode, P.small.K, P.small.mode, P.nblocks, P.NsP, PT, P.nstage, smem);
     for (int w = 0; w < tcm::NTHREADS / 32; ++w) {
       const unsigned long long* o = h + w * 8;
-      const char* role = w == 0 ? "mma+epi" : w < 4 ? "epi " : w == 4 ? "tma " : "prod";
+      const char* role = w == 0 ? "mma+epi" : w == 1 ? "tma+epi" : w < 4 ? "epi " : "prod";
       fprintf(stderr, "[wmdbg]  w%02d %s setup=%llu total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu\n", w, role, o[0], o[1],
               o[2], o[3], o[4], o[5], o[6]);
     }
