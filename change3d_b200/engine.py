@@ -21,6 +21,22 @@ from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_CONVT, EPI_RELU_ADD, EPI_STORE
                    PRO_MASK_POS, PRO_NONE)
 
 
+import os
+
+_SIDE = {"stream": None}
+
+
+def _side_stream():
+    """Second stream for the weight-gradient GEMMs of a block's backward (default on; C3D_SIDE_STREAM=0 disables): they only depend on
+    the BN-backward coefficients, not on the dgrad chain, so they can fill the SMs the tiny finalizer kernels and
+    kernel tails leave idle.  Forked and joined inside res_block_backward (also under CUDA-graph capture)."""
+    if os.environ.get("C3D_SIDE_STREAM", "1") != "1":
+        return None
+    if _SIDE["stream"] is None:
+        _SIDE["stream"] = torch.cuda.Stream()
+    return _SIDE["stream"]
+
+
 class StatArena:
     """One zero-filled fp64 buffer per stage call; the BN/SE statistics of every layer are carved
     out of it (a single memset instead of one per layer)."""
@@ -324,7 +340,14 @@ def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena,
                 stats=st_du, E1=s.y_b, ebnp=s.bnp_b, egate=s.gate, rows_per_sample=T * OH * OW)
     Q_c = ops.operand(s.y_b, ld=Cis, OH=OH, OW=OW, mode=PRO_BN_GATE_SWISH, bnp=s.bnp_b, gate=s.gate,
                       frames_per_sample=T)
-    ops.pw_wgrad(P_c, Q_c, M=M_out, dW=g_wc, dw_sn=Ci, dw_sk=1, N=Cout, K=Ci)
+    side = _side_stream()
+    main = torch.cuda.current_stream()
+    if side is not None:
+        side.wait_stream(main)                      # coef_c, d_pre are ready
+        with torch.cuda.stream(side):
+            ops.pw_wgrad(P_c, Q_c, M=M_out, dW=g_wc, dw_sn=Ci, dw_sk=1, N=Cout, K=Ci)
+    else:
+        ops.pw_wgrad(P_c, Q_c, M=M_out, dW=g_wc, dw_sn=Ci, dw_sk=1, N=Cout, K=Ci)
 
     # 3. SE backward + BN_b coefficients
     coef_b, dpool = ops.se_bn_bwd_finalize(st_du, N, T * OH * OW, s.bnp_b, b2.norm_b[0], se, s.gate, s.hidden,
@@ -335,6 +358,14 @@ def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena,
     dr = ops.dw_conv_bwd(du, s.y_b, s.bnp_b, s.gate if se is not None else None, dpool, coef_b, s.y_a, s.bnp_a,
                          b2.conv_b.weight, Ci, s.stride, st_a, g_wb)
     coef_a = ops.bn_bwd_finalize(st_a, 1, M_in, Ci, Cis, g_ga, g_ba)
+
+    # conv_a weight gradient: needs dr and coef_a only, so with a side stream it is queued before the dgrad kernels
+    P_a = ops.operand(dr, ld=Cis, OH=H, OW=W, mode=PRO_BNBWD, A2=s.y_a, bnp=s.bnp_a, coef=coef_a)
+    Q_a = ops.operand(s.x, ld=Cin, OH=H, OW=W)
+    if side is not None:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.pw_wgrad(P_a, Q_a, M=M_in, dW=g_wa, dw_sn=Cin, dw_sk=1, N=Ci, K=Cin)
 
     # 5. shortcut conv backward (first block of a stage)
     dx1 = None
@@ -350,12 +381,13 @@ def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena,
         ops.pw_wgrad(P_1, Q_1, M=M_out, dW=g_w1, dw_sn=Cin, dw_sk=1, N=Cout, K=Cin)
 
     # 6. conv_a backward; the epilogue joins the shortcut gradient
-    P_a = ops.operand(dr, ld=Cis, OH=H, OW=W, mode=PRO_BNBWD, A2=s.y_a, bnp=s.bnp_a, coef=coef_a)
     dx = torch.empty(N, T, H, W, Cin, device=dev, dtype=torch.float32)
     ops.pw_gemm(P_a, b2.conv_a.weight, w_sr=Cin, w_so=1, Kred=Ci, N=Cin, Ns=Cin, M=M_in, Y=dx, epi=EPI_ADD2,
                 E1=None if first else d_pre, E2=dx1)
-    Q_a = ops.operand(s.x, ld=Cin, OH=H, OW=W)
-    ops.pw_wgrad(P_a, Q_a, M=M_in, dW=g_wa, dw_sn=Cin, dw_sk=1, N=Ci, K=Cin)
+    if side is not None:
+        main.wait_stream(side)                      # join before this block's tensors can be released
+    else:
+        ops.pw_wgrad(P_a, Q_a, M=M_in, dW=g_wa, dw_sn=Cin, dw_sk=1, N=Ci, K=Cin)
     return dx
 
 
