@@ -161,7 +161,8 @@ int c3d_se_bn_bwd_finalize(const double* stats, int N, long long count_per_sampl
 /* conv_b backward (autograd of model/x3d.py:184-193 with BN_b/SE on its output and ReLU+BN_a on its input):
  * dy_b = scale_b*(du*gate + dpool - c1 - zhat*c2); dr = conv_transpose(dy_b, w) * (bn_a(y_a) > 0);
  * dW[C][27] += (fp32 atomics, caller zeroes); stats_a[2][Cs] += (sum dr, sum dr*yhat_a).
- * `du` is scratch: it is overwritten with dy_b by the elementwise pre-pass. */
+ * `du` is scratch: the stride-2 and fallback paths overwrite it with dy_b in an elementwise pre-pass (the stride-1
+ * row-streaming kernel applies that transform while it stages the rows and leaves du untouched). */
 int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, const float* gate, const float* dpool,
                     const float* coef_b, const float* y_a, const float* bnp_a, const float* w, float* dr, float* dW,
                     double* stats_a, int N, int T, int IH, int IW, int C, int Cs, int stride, void* cuda_stream);
