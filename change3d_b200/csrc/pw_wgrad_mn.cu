@@ -358,6 +358,10 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   // the big operand's last block may read (never use) up to 3 groups past its own: keep the small operand behind it
   const int groups = P.Gb + P.Gs;
   int PT = groups <= 3 ? 64 : groups <= 6 ? 32 : 16;
+  {      // tuning override: C3D_WMN_PT = pixels per stage (multiple of 16)
+    static const int pt_env = getenv("C3D_WMN_PT") ? atoi(getenv("C3D_WMN_PT")) : 0;
+    if (pt_env >= 16 && (pt_env & 15) == 0 && pt_env <= 256) PT = pt_env;
+  }
   P.PT = PT;
   P.grp_bytes = (uint32_t)PT * 128u;
   P.off_blo = (uint32_t)P.Gb * P.grp_bytes;
