@@ -23,7 +23,7 @@ from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_CONVT, EPI_RELU_ADD, EPI_STORE
 
 import os
 
-_SIDE = {"stream": None}
+_SIDE = {}      # device index -> side stream
 
 
 def _side_stream():
@@ -32,9 +32,10 @@ def _side_stream():
     kernel tails leave idle.  Forked and joined inside res_block_backward (also under CUDA-graph capture)."""
     if os.environ.get("C3D_SIDE_STREAM", "1") != "1":
         return None
-    if _SIDE["stream"] is None:
-        _SIDE["stream"] = torch.cuda.Stream()
-    return _SIDE["stream"]
+    dev = torch.cuda.current_device()
+    if dev not in _SIDE:
+        _SIDE[dev] = torch.cuda.Stream(device=dev)
+    return _SIDE[dev]
 
 
 class StatArena:
