@@ -127,8 +127,12 @@ __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restric
                                                           const float* __restrict__ B, const float* __restrict__ bnpB,
                                                           float* __restrict__ Y, long long total4, int Cs) {
   const int q4 = Cs >> 2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % q4) * 4;
+  // channel quad of element i tracked incrementally (a 64-bit modulo per element costs more than the arithmetic)
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const int cstep = (int)(stride % (unsigned)q4) * 4;
+  int c = (int)(i0 % q4) * 4;
+  for (long long i = i0; i < total4; i += stride) {
     float4 v = f4bn(ldg4(A + i * 4), ldg4(bnpA + c), ldg4(bnpA + 2 * Cs + c), ldg4(bnpA + 3 * Cs + c));
     if (B) {
       float4 b = ldg4(B + i * 4);
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restric
       v = f4add(v, b);
     }
     st4(Y + i * 4, f4relu(v));
+    c += cstep;
+    if (c >= Cs) c -= Cs;
   }
 }
 
