@@ -300,6 +300,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"BCD X3D-L train (fwd+BCEDiceLoss+bwd+Adam), synthetic LEVIR-shape {S}x{S}, "
                                        f"batch {B}/GPU, T=3", "global_batch": world * B, "parallelism": f"dp{world}",
+                           "gemm_arithmetic": "3xTF32 split products on tcgen05, fp32 accumulate (fp32-class)",
                            "cuda_graph": not args.no_graph, "wgrad_side_stream": os.environ.get("C3D_SIDE_STREAM", "1") == "1",
                            "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed"},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
