@@ -123,6 +123,55 @@ def test_convtranspose_pack_index_reproduces_conv_transpose2d():
     assert torch.allclose(out, ref, atol=1e-5)
 
 
+def test_convtranspose_as_gemm_col2im_im2col_matches_torch():
+    """The decoder's ConvTranspose2d(k4, s2, p1) formulation (engine.decoder_up_forward / _backward):
+    U = t x W_all over the input grid, out = bias + skip + col2im(U); backward V = im2col(d_out),
+    d t = V x W_all^T, d W_all = t^T x V.  Restated here with torch index arithmetic exactly as the kernels in
+    csrc/decoder.cu index (2j-1+ky = y, 2i-1+kx = x) and compared with F.conv_transpose2d and its autograd
+    (reference: model/change_decoder.py:30-45,71-73)."""
+    cmid, cout, B, h, w = 6, 4, 2, 3, 5
+    g = torch.Generator().manual_seed(3)
+    wt = torch.randn(cmid, cout, 4, 4, generator=g).double().requires_grad_(True)
+    bias = torch.randn(cout, generator=g).double()
+    t = torch.randn(B, cmid, h, w, generator=g).double().requires_grad_(True)
+    skip = torch.randn(B, cout, 2 * h, 2 * w, generator=g).double()
+    d_out = torch.randn(B, cout, 2 * h, 2 * w, generator=g).double()
+    ref = F.conv_transpose2d(t, wt, bias, stride=2, padding=1) + skip
+    ref.backward(d_out)
+
+    w_all = wt.detach().permute(0, 2, 3, 1).reshape(cmid, 16 * cout)            # [ci][(ky,kx,co)]
+    tn = t.detach().permute(0, 2, 3, 1)                                          # NHWC
+    U = (tn.reshape(-1, cmid) @ w_all).view(B, h, w, 4, 4, cout)
+    out = (bias.view(1, 1, 1, cout) + skip.permute(0, 2, 3, 1)).clone()
+    for y in range(2 * h):
+        for x in range(2 * w):
+            for a in range(2):
+                ky = ((y + 1) & 1) + 2 * a
+                if y + 1 - ky < 0 or (y + 1 - ky) // 2 >= h:
+                    continue
+                for e in range(2):
+                    kx = ((x + 1) & 1) + 2 * e
+                    if x + 1 - kx < 0 or (x + 1 - kx) // 2 >= w:
+                        continue
+                    out[:, y, x] += U[:, (y + 1 - ky) // 2, (x + 1 - kx) // 2, ky, kx]
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref.detach(), atol=1e-10)
+
+    dn = d_out.permute(0, 2, 3, 1)
+    V = torch.zeros(B, h, w, 4, 4, cout, dtype=torch.float64)
+    for ky in range(4):
+        for kx in range(4):
+            for j in range(h):
+                for i in range(w):
+                    y, x = 2 * j - 1 + ky, 2 * i - 1 + kx
+                    if 0 <= y < 2 * h and 0 <= x < 2 * w:
+                        V[:, j, i, ky, kx] = dn[:, y, x]
+    Vm = V.reshape(-1, 16 * cout)
+    d_t = (Vm @ w_all.t()).view(B, h, w, cmid).permute(0, 3, 1, 2)
+    d_w = (tn.reshape(-1, cmid).t() @ Vm).view(cmid, 4, 4, cout).permute(0, 3, 1, 2)
+    assert torch.allclose(d_t, t.grad, atol=1e-10)
+    assert torch.allclose(d_w, wt.grad, atol=1e-10)
+
+
 def test_lr_schedule_matches_oracle():
     from change3d_b200.model.utils import adjust_learning_rate
     args = argparse.Namespace(lr_mode="poly", lr=2e-4, max_epochs=10, step_loss=None)
