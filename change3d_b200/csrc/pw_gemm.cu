@@ -299,7 +299,6 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const WgradArgs g) {
 // host side
 // ------------------------------------------------------------------------------------------
 int c3d_launch_pw_gemm_tc(const GemmArgs& g, int num_sms, cudaStream_t stream, int lbo_is_k, int compact, int use_tma);   // pw_gemm_tc.cu
-int c3d_launch_pw_gemm_tw(const GemmArgs& g, int num_sms, cudaStream_t stream, int dbg);                   // pw_gemm_tw.cu
 int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
                            int N, int K, int num_sms, cudaStream_t stream, int desc_swap);          // pw_wgrad_tc.cu
 int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, float* dW, long long dw_sn, long long dw_sk,
@@ -367,10 +366,6 @@ extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   const int ncls = d->epi == EPI_CONVT ? 4 : 1;
   if (env_flag("C3D_TC", 1)) {
     g.NB = 0; g.nsplit = 1;
-    if (env_flag("C3D_TC_KIND", 1) == 2) {      // experimental weights-in-TMEM formulation (slower: see DESIGN.md)
-      const int rw = c3d_launch_pw_gemm_tw(g, num_sms(), stream, env_flag("C3D_TW_DBG", 0));
-      if (rw >= 0) return rw;
-    }
     const int r = c3d_launch_pw_gemm_tc(g, num_sms(), stream, env_flag("C3D_TC_LBO", 1) | (env_flag("C3D_TC_HINT", 0) << 1),
                                             env_flag("C3D_TC_COMPACT", 1), env_flag("C3D_TC_TMA", 1));
     if (r >= 0) return r;

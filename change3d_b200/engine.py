@@ -251,9 +251,9 @@ def decoder_forward(dec, feats, save: bool):
     c3, s3 = feature_view(feats[2].float())
     c4, s4 = feature_view(feats[3].float())
     h4, w4 = feats[3].shape[2], feats[3].shape[3]
-    c3f, t4 = decoder_up_forward(dec.up_c4, c4, s4, h4, w4, c3, s3, dec.pack_index("up_c4"))
-    c2f, t3 = decoder_up_forward(dec.up_c3, c3f, c3f[0].numel(), 2 * h4, 2 * w4, c2, s2, dec.pack_index("up_c3"))
-    c1f, t2 = decoder_up_forward(dec.up_c2, c2f, c2f[0].numel(), 4 * h4, 4 * w4, c1, s1, dec.pack_index("up_c2"))
+    c3f, t4 = decoder_up_forward(dec.up_c4, c4, s4, h4, w4, c3, s3)
+    c2f, t3 = decoder_up_forward(dec.up_c3, c3f, c3f[0].numel(), 2 * h4, 2 * w4, c2, s2)
+    c1f, t2 = decoder_up_forward(dec.up_c2, c2f, c2f[0].numel(), 4 * h4, 4 * w4, c1, s1)
     pred = ops.dec_head_fwd(c1f, dec.up_c1[0].weight, dec.has_sigmoid)
     saved = None
     if save:
