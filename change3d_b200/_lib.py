@@ -67,7 +67,17 @@ SIGNATURES = {
                      _i, _i, _i, _i, _fp],
     "c3d_dec_head_bwd": [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _fp],
     "c3d_adam_step": [_fp, _fp, _fp, _fp, _ll, _f, _f, _f, _f, _f, _i, _f, _fp],
+    "c3d_bce_dice_fwd": [_fp, _fp, _ll, _fp, _fp, _fp, _fp],
+    "c3d_bce_dice_bwd": [_fp, _fp, _fp, _fp, _f, _fp, _ll, _fp],
+    "c3d_ce2d_fwd": [_fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _fp, _fp, _fp, _fp],
+    "c3d_ce2d_bwd": [_fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _fp, _f, _fp, _fp],
+    "c3d_change_similarity_fwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _fp, _fp],
+    "c3d_change_similarity_bwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _f, _fp, _fp, _fp],
+    "c3d_confusion_matrix": [_fp, _i, _fp, _ll, _i, _fp, _fp],
 }
+
+LOSS_WS_BYTES = 128      # C3D_LOSS_WS_BYTES
+LOSS_OUT_FLOATS = 8      # C3D_LOSS_OUT_FLOATS
 
 _lib = None
 

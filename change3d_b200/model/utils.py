@@ -1,9 +1,10 @@
 """Host-side helpers with the reference's names and semantics (model/utils.py): weight_init,
-adjust_learning_rate, BCEDiceLoss.  Loss arithmetic on the (B,1,H,W) prediction is not part of the
-X3D kernel path (SURVEY.md §8f "next" row 1); it uses torch ops until the fused loss kernel lands."""
+adjust_learning_rate, and the losses BCEDiceLoss / CrossEntropyLoss2d / ChangeSimilarity, which run as fused
+sm_100a kernels (change3d_b200/losses.py, csrc/loss.cu) — CUDA tensors only."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+
+from ..losses import ChangeSimilarity, CrossEntropyLoss2d, bce_dice_loss  # noqa: F401  (reference names)
 
 
 def weight_init(module):
@@ -64,9 +65,5 @@ def adjust_learning_rate(args, optimizer, epoch=None, iter=None, max_batches=Non
 
 
 def BCEDiceLoss(inputs, targets):
-    """model/utils.py:154-169."""
-    bce = F.binary_cross_entropy(inputs, targets)
-    inter = (inputs * targets).sum()
-    eps = 1e-5
-    dice = (2 * inter + eps) / (inputs.sum() + targets.sum() + eps)
-    return bce + 1 - dice
+    """model/utils.py:154-169: F.binary_cross_entropy(inputs, targets) + 1 - dice, one fused kernel each way."""
+    return bce_dice_loss(inputs, targets)

@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .model.utils import BCEDiceLoss
+from .losses import bce_dice_loss
 
 
 def _trained_parameters(model) -> List[torch.nn.Parameter]:
@@ -53,6 +53,8 @@ class FlatAdam:
         self.m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.v = torch.zeros(total, device=dev, dtype=torch.float32)
         self.step_count = 0
+        # `adjust_learning_rate` (model/utils.py:84-150) writes param_groups[i]['lr']; step() reads it back
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
         off = 0
         gview = {}
         for p, n in zip(self.params, sizes):
@@ -93,16 +95,34 @@ class FlatAdam:
     def step(self, lr: Optional[float] = None) -> None:
         self.step_count += 1
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr if lr is None else lr, self.betas[0],
+        ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.param_groups[0]["lr"] if lr is None else lr, self.betas[0],
                       self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / world)
 
 
+    def state_dict(self) -> dict:
+        """Optimizer state for the reference's checkpoint dict (scripts/train_BCD.py:333-343 saves it, nothing in the
+        reference restores it): flat moment buffers + step + hyper-parameters."""
+        return {"state": {"step": self.step_count, "exp_avg": self.m.clone(), "exp_avg_sq": self.v.clone()},
+                "param_groups": [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.step_count = int(sd["state"]["step"])
+        self.m.copy_(sd["state"]["exp_avg"])
+        self.v.copy_(sd["state"]["exp_avg_sq"])
+        self.param_groups[0].update(sd["param_groups"][0])
+
+
 class BCDTrainStep:
-    """model.update_bcd -> BCEDiceLoss -> backward -> (all-reduce) -> fused Adam, optionally as a CUDA graph."""
+    """model.update_bcd -> BCEDiceLoss -> backward -> (all-reduce) -> fused Adam, optionally as a CUDA graph.
+
+    The loss kernel also accumulates the training confusion matrix hist[target][output > 0.5] into `self.cm`
+    (int64 (2,2), device) — the per-step `eval_meter.update_cm(pred.cpu().numpy(), target.cpu().numpy())` of
+    scripts/train_BCD.py:203-225 without leaving the GPU; read it with `scores()` at the end of an epoch."""
 
     def __init__(self, model, lr: float = 2e-4, use_graph: bool = False):
         self.model = model.train()
         self.opt = FlatAdam(model, lr=lr)
+        self.cm = torch.zeros(2, 2, dtype=torch.int64, device=self.opt.flat_p.device)
         self.use_graph = use_graph
         self.graph = None
         self.static = None
@@ -111,7 +131,7 @@ class BCDTrainStep:
     def _iteration(self, pre, post, target) -> torch.Tensor:
         self.opt.zero_grad()
         out = self.model.update_bcd(pre, post)
-        loss = BCEDiceLoss(out, target)
+        loss = bce_dice_loss(out, target, cm=self.cm)
         loss.backward()
         return loss.detach()
 
@@ -138,6 +158,7 @@ class BCDTrainStep:
             with torch.cuda.graph(self.graph):
                 self.loss = self._iteration(*self.static)
             self.captured_launches = _lib.LAUNCHES[0] - n0 + 1      # + the Adam launch outside the graph
+            self.cm.zero_()                                         # drop the warm-up iteration's counts
         for dst, src in zip(self.static, (pre, post, target)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -145,3 +166,8 @@ class BCDTrainStep:
         self.opt.all_reduce()
         self.opt.step(lr)                 # Adam outside the graph: step count / lr change every iteration
         return self.loss
+
+    def scores(self) -> dict:
+        """cm2score of the accumulated training confusion matrix (one small device->host copy)."""
+        from .metrics import cm2score
+        return cm2score(self.cm.cpu().numpy())

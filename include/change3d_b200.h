@@ -200,6 +200,54 @@ int c3d_convt_im2col(const float* d_out, float* V, int B, int h, int w, int cout
 int c3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* cuda_stream);
 
+/* ============================== losses and metrics ==============================
+ * Every forward is one streaming pass: partial sums go to a small device workspace `ws` (C3D_LOSS_WS_BYTES,
+ * zeroed ONCE by the caller; the kernels leave it zeroed), the last CTA writes the loss and the backward
+ * coefficients to `out` (device, float[C3D_LOSS_OUT_FLOATS]); nothing is read back to the host.
+ * `gout` = device pointer to the upstream scalar gradient (NULL = 1), multiplied by the host float `gscale`. */
+#define C3D_LOSS_WS_BYTES 128
+#define C3D_LOSS_OUT_FLOATS 8
+
+/* BCEDiceLoss (model/utils.py:154-169): out[0] = BCE(pred, target) + 1 - dice, out[4] = BCE, out[5] = dice,
+ * out[1..3] = coefficients for the backward.  pred = probabilities (after the head's sigmoid), target in {0,1},
+ * n elements.  When cm != NULL the same pass adds the 2x2 confusion matrix of (target, pred > 0.5) to
+ * cm[2*gt + pr] (long long[4]) -- the `torch.where(output > 0.5, ...)` mask + ConfuseMatrixMeter.update_cm of
+ * scripts/train_BCD.py:203-225 / utils/metric_tool.py:111-128 without the device->host copy. */
+int c3d_bce_dice_fwd(const float* pred, const float* target, long long n, void* ws, float* out, long long* cm,
+                     void* cuda_stream);
+/* dpred[i] = g * dLoss/dpred[i]  (autograd of model/utils.py:154-169; BCE gradient clamped like aten: / max(p(1-p), 1e-12)) */
+int c3d_bce_dice_bwd(const float* pred, const float* target, const float* out, const float* gout, float gscale,
+                     float* dpred, long long n, void* cuda_stream);
+
+/* CrossEntropyLoss2d (model/utils.py:171-178): NLLLoss(log_softmax(logits, dim 1), target, ignore_index, 'mean').
+ * logits (B, C, HW) with batch_stride elements between samples (0 = C*HW; lets `mask[:, 1:]`-style views pass),
+ * C <= 16; target int64 (B, HW).  out[0] = loss (nan when every pixel is ignored, like torch), out[1] = 1/count.
+ * Optional: argmax_out int64 (B, HW) = torch.argmax(logits, 1) (scripts/train_SCD.py:243-244);
+ * cm long long[C*C] += histogram of (target, argmax) over pixels with 0 <= target < C. */
+int c3d_ce2d_fwd(const float* logits, const long long* target, int B, int C, long long HW, long long batch_stride,
+                 long long ignore_index, void* ws, float* out, long long* argmax_out, long long* cm,
+                 void* cuda_stream);
+/* dlogits dense (B, C, HW) = g * (softmax - onehot) / count on counted pixels, 0 on ignored ones. */
+int c3d_ce2d_bwd(const float* logits, const long long* target, int B, int C, long long HW, long long batch_stride,
+                 long long ignore_index, const float* out, const float* gout, float gscale, float* dlogits,
+                 void* cuda_stream);
+
+/* ChangeSimilarity (model/utils.py:180-203): CosineEmbeddingLoss(margin 0, 'mean') between softmax(x1) and
+ * softmax(x2) per pixel, target +1 where label_change == 0 and -1 elsewhere.  x1/x2 (B, C, HW) with their own
+ * batch strides (the scripts pass `pre_mask[:, 1:]`, scripts/train_SCD.py:228); label_change int64 (B, HW).
+ * out[0] = loss.  Backward writes dense dx1, dx2 (B, C, HW). */
+int c3d_change_similarity_fwd(const float* x1, const float* x2, const long long* label_change, int B, int C,
+                              long long HW, long long batch_stride1, long long batch_stride2, void* ws, float* out,
+                              void* cuda_stream);
+int c3d_change_similarity_bwd(const float* x1, const float* x2, const long long* label_change, int B, int C,
+                              long long HW, long long batch_stride1, long long batch_stride2, const float* gout,
+                              float gscale, float* dx1, float* dx2, void* cuda_stream);
+
+/* get_confuse_matrix (utils/metric_tool.py:111-128): cm[num_classes*gt + pred] += 1 over the n entries with
+ * 0 <= gt < num_classes (gt float32 when gt_is_float, else int64; pred int64).  num_classes <= 16. */
+int c3d_confusion_matrix(const void* gt, int gt_is_float, const long long* pred, long long n, int num_classes,
+                         long long* cm, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -362,3 +363,51 @@ def clone_sd(sd: StateDict, dtype=None, requires_grad: bool = False) -> StateDic
             t.requires_grad_(True)
         out[k] = t
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Losses and metrics of the train step — restated; pinned to the reference's own functions by
+# tests/golden/losses.npz (oracle/make_golden_losses.py).
+def cross_entropy_2d(inputs: Tensor, targets: Tensor, ignore_index: int = -1) -> Tensor:
+    """CrossEntropyLoss2d (model/utils.py:171-178): mean over non-ignored pixels of -log_softmax(inputs, 1)[target]."""
+    logp = inputs - torch.logsumexp(inputs, dim=1, keepdim=True)
+    valid = targets != ignore_index
+    picked = logp.gather(1, targets.clamp(min=0).unsqueeze(1)).squeeze(1)
+    return -(picked * valid).sum() / valid.sum()
+
+
+def change_similarity(x1: Tensor, x2: Tensor, label_change: Tensor) -> Tensor:
+    """ChangeSimilarity (model/utils.py:180-203): CosineEmbeddingLoss(margin 0, mean) between the per-pixel class
+    distributions; target +1 on unchanged pixels (1 - cos), -1 on changed pixels (max(0, cos))."""
+    b, c, h, w = x1.shape
+    p1 = torch.softmax(x1, dim=1).permute(0, 2, 3, 1).reshape(b * h * w, c)
+    p2 = torch.softmax(x2, dim=1).permute(0, 2, 3, 1).reshape(b * h * w, c)
+    changed = label_change.reshape(b * h * w).bool()
+    eps = 1e-12                                          # aten cosine_embedding_loss EPSILON
+    cos = (p1 * p2).sum(1) / torch.sqrt(((p1 * p1).sum(1) + eps) * ((p2 * p2).sum(1) + eps))
+    per = torch.where(changed, cos.clamp(min=0), 1 - cos)
+    return per.mean()
+
+
+def confusion_matrix(num_classes: int, label_gt, label_pred) -> np.ndarray:
+    """get_confuse_matrix for one batch (utils/metric_tool.py:111-128): hist[gt][pred] over 0 <= gt < num_classes."""
+    gt = np.asarray(label_gt).reshape(-1)
+    pr = np.asarray(label_pred).reshape(-1)
+    mask = (gt >= 0) & (gt < num_classes)
+    return np.bincount(num_classes * gt[mask].astype(int) + pr[mask], minlength=num_classes ** 2) \
+        .reshape(num_classes, num_classes).astype(np.int64)
+
+
+def cm_scores(cm) -> dict:
+    """cm2score (utils/metric_tool.py:84-108)."""
+    hist = np.asarray(cm, dtype=np.float64)
+    e = np.finfo(np.float32).eps
+    tp, fn, fp, tn = hist[1, 1], hist[1, 0], hist[0, 1], hist[0, 0]
+    oa = (tp + tn) / (tp + fn + fp + tn + e)
+    recall = tp / (tp + fn + e)
+    precision = tp / (tp + fp + e)
+    f1 = 2 * recall * precision / (recall + precision + e)
+    iou = tp / (tp + fp + fn + e)
+    pre = ((tp + fn) * (tp + fp) + (tn + fp) * (tn + fn)) / (tp + fp + tn + fn) ** 2
+    kappa = (oa - pre) / (1 - pre)
+    return {'Kappa': kappa, 'IoU': iou, 'F1': f1, 'OA': oa, 'recall': recall, 'precision': precision, 'Pre': pre}

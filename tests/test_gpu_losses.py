@@ -1,0 +1,217 @@
+"""GPU parity of the fused loss / metric kernels (csrc/loss.cu, through the C ABI) against the oracle and the
+reference-generated golden vectors (tests/golden/losses.npz).  Tolerances: losses 1e-5 relative (fp64 reductions
+of fp32 terms), gradients rtol 2e-4 per element (fp32 logf/expf vs torch's), confusion matrices / argmax maps
+bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import change3d_oracle as O
+from tests.gpu_util import log
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "losses.npz"))
+
+
+def _close(name, got, ref, rtol=2e-4, atol=1e-9):
+    got = got.detach().cpu().double().numpy() if torch.is_tensor(got) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().cpu().double().numpy() if torch.is_tensor(ref) else np.asarray(ref, dtype=np.float64)
+    err = np.abs(got - ref) / (atol / rtol + np.abs(ref))
+    log(f"losses/{name}: max per-element rel err {err.max():.3e} (rtol {rtol:.1e})")
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol)
+
+
+def test_bce_dice_golden(g):
+    from change3d_b200 import losses
+    from change3d_b200.model.utils import BCEDiceLoss
+    p = torch.tensor(g["bce_pred"], device=DEV, requires_grad=True)
+    t = torch.tensor(g["bce_target"], device=DEV)
+    cm = torch.zeros(2, 2, dtype=torch.int64, device=DEV)
+    loss, parts = losses.bce_dice_loss(p, t, cm=cm, return_parts=True)
+    (loss * 1.0).backward()
+    assert abs(loss.item() - float(g["bce_loss"])) < 1e-5 * abs(float(g["bce_loss"]))
+    assert abs((parts[4] + 1 - parts[5]).item() - loss.item()) < 1e-6
+    _close("bce_grad_golden", p.grad, g["bce_grad"])
+    assert np.array_equal(cm.cpu().numpy(), g["bce_cm"])
+    # the reference-named entry point, twice (workspace must be left clean), and accumulation into cm
+    for _ in range(2):
+        l2 = BCEDiceLoss(p.detach(), t)
+        assert l2.item() == loss.item()
+    losses.bce_dice_loss(p.detach(), t, cm=cm)
+    assert np.array_equal(cm.cpu().numpy(), 2 * g["bce_cm"])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 7, 5), (2, 1, 33, 31), (4, 1, 256, 256)])
+def test_bce_dice_vs_oracle(shape):
+    from change3d_b200 import losses
+    gen = torch.Generator().manual_seed(sum(shape))
+    p = torch.sigmoid(torch.randn(*shape, generator=gen) * 4)
+    t = (torch.rand(*shape, generator=gen) < 0.05).float()
+    p64 = p.double().requires_grad_(True)
+    ref = O.bce_dice_loss(p64, t.double())
+    ref.backward()
+    pg = p.to(DEV).requires_grad_(True)
+    cm = torch.zeros(4, dtype=torch.int64, device=DEV)
+    up = torch.tensor(0.37, device=DEV)
+    loss = losses.bce_dice_loss(pg, t.to(DEV), cm=cm)
+    (loss * up).backward()                                   # non-unit upstream gradient read from the device
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    _close(f"bce_grad{shape}", pg.grad, 0.37 * p64.grad)
+    want = O.confusion_matrix(2, t.numpy(), (p > 0.5).long().numpy())
+    assert np.array_equal(cm.view(2, 2).cpu().numpy(), want)
+
+
+def test_bce_dice_unaligned_and_odd_sizes():
+    """Scalar path: views that are not 16-byte aligned / sizes that are not a multiple of 4."""
+    from change3d_b200 import losses
+    gen = torch.Generator().manual_seed(3)
+    base_p = torch.sigmoid(torch.randn(1031, generator=gen)).to(DEV)
+    base_t = (torch.rand(1031, generator=gen) < 0.3).float().to(DEV)
+    for off, n in ((1, 1030), (0, 1029), (3, 1)):
+        p = base_p[off:off + n].detach().requires_grad_(True)
+        t = base_t[off:off + n]
+        ref_p = base_p[off:off + n].detach().cpu().double().requires_grad_(True)
+        ref = O.bce_dice_loss(ref_p, t.cpu().double())
+        ref.backward()
+        loss = losses.bce_dice_loss(p, t)
+        loss.backward()
+        assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+        _close(f"bce_unaligned_{off}_{n}", p.grad, ref_p.grad)
+
+
+def test_ce2d_and_similarity_golden(g):
+    from change3d_b200 import losses
+    from change3d_b200.model.utils import ChangeSimilarity, CrossEntropyLoss2d
+    pre = torch.tensor(g["scd_pre"], device=DEV, requires_grad=True)
+    post = torch.tensor(g["scd_post"], device=DEV, requires_grad=True)
+    lc = torch.tensor(g["scd_label_change"], device=DEV)
+    lab = torch.tensor(g["scd_pre_label"], device=DEV)
+    seg = CrossEntropyLoss2d(ignore_index=0)(pre, lab)
+    sim = ChangeSimilarity()(pre[:, 1:], post[:, 1:], lc.unsqueeze(1))          # strided views, as the script passes
+    (seg * 0.5 + sim).backward()
+    assert abs(seg.item() - float(g["scd_seg_loss"])) < 1e-5 * float(g["scd_seg_loss"])
+    assert abs(sim.item() - float(g["scd_sim_loss"])) < 1e-5 * float(g["scd_sim_loss"])
+    _close("scd_pre_grad", pre.grad, g["scd_pre_grad"], atol=1e-8)
+    _close("scd_post_grad", post.grad, g["scd_post_grad"], atol=1e-8)
+    # argmax map + confusion matrix from the same pass: bit-exact
+    am = torch.empty(lab.shape, dtype=torch.int64, device=DEV)
+    cm = torch.zeros(7, 7, dtype=torch.int64, device=DEV)
+    l2 = losses.cross_entropy_2d(pre.detach(), lab, ignore_index=0, argmax_out=am, cm=cm)
+    assert l2.item() == seg.item()
+    assert np.array_equal(am.cpu().numpy(), g["scd_argmax"])
+    assert np.array_equal(cm.cpu().numpy(), g["scd_cm"])
+    assert np.array_equal(losses.confusion_matrix(lab, am, 7).cpu().numpy(), g["scd_cm"])
+    # BDA-shaped case, both ignore_index settings
+    x = torch.tensor(g["bda_x"], device=DEV, requires_grad=True)
+    t = torch.tensor(g["bda_t"], device=DEV)
+    for ign, key in ((0, "ign0"), (-1, "ignm1")):
+        x.grad = None
+        loss = CrossEntropyLoss2d(ignore_index=ign)(x, t)
+        loss.backward()
+        assert abs(loss.item() - float(g["bda_loss_" + key])) < 1e-5 * float(g["bda_loss_" + key])
+        _close("bda_grad_" + key, x.grad, g["bda_grad_" + key], atol=1e-8)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 7, 64, 64), (1, 5, 17, 13), (2, 12, 9, 11), (16, 7, 256, 256)])
+def test_ce2d_and_similarity_vs_oracle(B, C, H, W):
+    from change3d_b200 import losses
+    gen = torch.Generator().manual_seed(B * 1000 + C * 100 + H)
+    x1 = torch.randn(B, C, H, W, generator=gen) * 2
+    x2 = torch.randn(B, C, H, W, generator=gen) * 2
+    lc = (torch.rand(B, H, W, generator=gen) < 0.2).long()
+    lab = torch.randint(1, C, (B, H, W), generator=gen) * lc
+    a64, b64 = x1.double().requires_grad_(True), x2.double().requires_grad_(True)
+    ref_seg = O.cross_entropy_2d(a64, lab, ignore_index=0)
+    ref_sim = O.change_similarity(a64[:, 1:], b64[:, 1:], lc.unsqueeze(1))
+    (ref_seg + ref_sim).backward()
+    a, b = x1.to(DEV).requires_grad_(True), x2.to(DEV).requires_grad_(True)
+    am = torch.empty(B, H, W, dtype=torch.int64, device=DEV)
+    seg = losses.cross_entropy_2d(a, lab.to(DEV), ignore_index=0, argmax_out=am)
+    sim = losses.ChangeSimilarity()(a[:, 1:], b[:, 1:], lc.to(DEV).unsqueeze(1))
+    (seg + sim).backward()
+    assert abs(seg.item() - ref_seg.item()) < 1e-5 * abs(ref_seg.item())
+    assert abs(sim.item() - ref_sim.item()) < 1e-5 * abs(ref_sim.item())
+    _close(f"ce_sim_grad_a{(B, C, H, W)}", a.grad, a64.grad, atol=1e-10)
+    _close(f"ce_sim_grad_b{(B, C, H, W)}", b.grad, b64.grad, atol=1e-10)
+    assert torch.equal(am.cpu(), torch.argmax(x1, dim=1))
+
+
+def test_ce2d_all_ignored_is_nan_and_zero_grad():
+    from change3d_b200 import losses
+    x = torch.randn(1, 5, 4, 4, device=DEV, requires_grad=True)
+    t = torch.zeros(1, 4, 4, dtype=torch.int64, device=DEV)
+    loss = losses.cross_entropy_2d(x, t, ignore_index=0)
+    loss.backward()
+    assert torch.isnan(loss).item()                      # torch: mean over zero pixels
+    assert torch.count_nonzero(x.grad).item() == 0
+    l2 = losses.cross_entropy_2d(x.detach(), t + 1, ignore_index=0)      # workspace left clean after the nan
+    assert torch.isfinite(l2).item()
+
+
+def test_confusion_meter_matches_reference_semantics():
+    from change3d_b200.metrics import ConfuseMatrixMeter
+    gen = torch.Generator().manual_seed(5)
+    meter = ConfuseMatrixMeter(2, device=DEV)
+    total = np.zeros((2, 2), dtype=np.int64)
+    for _ in range(3):
+        gt = (torch.rand(2, 1, 50, 41, generator=gen) < 0.3).float()
+        pr = (torch.rand(2, 1, 50, 41, generator=gen) < 0.4).long()
+        meter.update_cm(pr.to(DEV), gt.to(DEV))
+        cur = O.confusion_matrix(2, gt.numpy(), pr.numpy())
+        total += cur
+        assert np.array_equal(meter.val.cpu().numpy(), cur)
+    assert np.array_equal(meter.sum.cpu().numpy(), total)
+    ref = O.cm_scores(total)
+    got = meter.get_scores()
+    assert all(abs(got[k] - ref[k]) < 1e-12 for k in ref)
+    # out-of-range labels are masked like (gt >= 0) & (gt < n)
+    gt = torch.tensor([0., 1., 2., -1., 1.], device=DEV)
+    pr = torch.tensor([0, 1, 1, 0, 0], device=DEV)
+    meter.clear()
+    meter.update_cm(pr, gt)
+    assert meter.sum.cpu().tolist() == [[1, 0], [1, 1]]
+
+
+def test_train_step_confusion_matrix_eager_and_graph():
+    """BCDTrainStep: the loss kernel's on-device confusion matrix equals the reference's per-step
+    `torch.where(output > 0.5)` + get_confuse_matrix on the same predictions, and the CUDA-graph replay
+    accumulates the same matrix and the same losses as the eager step."""
+    from change3d_b200.train_step import BCDTrainStep
+    from tests.gpu_util import build_trainer
+    B, H, W = 2, 64, 64
+    pre, post, target = O.synth_inputs(B, H, W, 7)
+    pre, post, target = pre.to(DEV), post.to(DEV), target.to(DEV)
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(16)
+        model = build_trainer("bcd", H, W, 1).train()
+        if not use_graph:
+            with torch.no_grad():
+                first_pred = model.update_bcd(pre, post)       # train-mode forward also moves the running stats,
+            torch.manual_seed(16)                              # so rebuild the model for the timed comparison
+            model = build_trainer("bcd", H, W, 1).train()
+            want_first = O.confusion_matrix(2, target.cpu().numpy(), (first_pred > 0.5).long().cpu().numpy())
+        step = BCDTrainStep(model, lr=2e-4, use_graph=use_graph)
+        losses_, cms = [], []
+        for _ in range(3):
+            losses_.append(step(pre, post, target).item())
+            cms.append(step.cm.cpu().numpy().copy())
+        assert cms[-1].sum() == 3 * B * H * W
+        if not use_graph:
+            assert np.array_equal(cms[0], want_first)
+        sc = step.scores()
+        ref = O.cm_scores(cms[-1])
+        assert all(abs(sc[k] - ref[k]) < 1e-12 or (np.isnan(sc[k]) and np.isnan(ref[k])) for k in ref)
+        results.append((losses_, cms))
+    (l_e, cm_e), (l_g, cm_g) = results
+    log("train-step losses eager " + " ".join(f"{v:.5f}" for v in l_e) + " | graph " + " ".join(f"{v:.5f}" for v in l_g))
+    assert np.array_equal(cm_e[0], cm_g[0])                    # first step: identical weights, identical mask
+    assert abs(l_e[0] - l_g[0]) < 1e-5 and all(abs(a - b) < 5e-3 for a, b in zip(l_e, l_g))
+    assert l_e[-1] < l_e[0]
