@@ -135,14 +135,17 @@ class BCDTrainStep:
         loss.backward()
         return loss.detach()
 
+    def eager(self, pre: torch.Tensor, post: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None):
+        """One iteration without the graph (any batch size — e.g. the ragged last batch of an epoch)."""
+        loss = self._iteration(pre, post, target)
+        self.opt.all_reduce()
+        self.opt.step(lr)
+        return loss
+
     def __call__(self, pre: torch.Tensor, post: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None):
         """pre/post (B,3,H,W), target (B,1,H,W) on the GPU.  Returns the (device) loss of this iteration."""
-        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         if not self.use_graph:
-            loss = self._iteration(pre, post, target)
-            self.opt.all_reduce()
-            self.opt.step(lr)
-            return loss
+            return self.eager(pre, post, target, lr)
         if self.graph is None:
             # warm-up on a side stream (also sets every kernel's shared-memory attribute), then capture
             self.static = (pre.clone(), post.clone(), target.clone())
@@ -155,7 +158,8 @@ class BCDTrainStep:
             from . import _lib
             n0 = _lib.LAUNCHES[0]
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: a DataLoader pin-memory thread may call cudaHostAlloc while this thread captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.loss = self._iteration(*self.static)
             self.captured_launches = _lib.LAUNCHES[0] - n0 + 1      # + the Adam launch outside the graph
             self.cm.zero_()                                         # drop the warm-up iteration's counts
