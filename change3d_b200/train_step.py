@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .losses import bce_dice_loss
+from .losses import ChangeSimilarity, bce_dice_loss, cross_entropy_2d
 
 
 def _trained_parameters(model) -> List[torch.nn.Parameter]:
@@ -112,43 +112,73 @@ class FlatAdam:
         self.param_groups[0].update(sd["param_groups"][0])
 
 
-class BCDTrainStep:
-    """model.update_bcd -> BCEDiceLoss -> backward -> (all-reduce) -> fused Adam, optionally as a CUDA graph.
+class TrainStep:
+    """model.update_<task> -> the script's loss -> backward -> (all-reduce) -> fused Adam, optionally as a CUDA graph.
 
-    The loss kernel also accumulates the training confusion matrix hist[target][output > 0.5] into `self.cm`
-    (int64 (2,2), device) — the per-step `eval_meter.update_cm(pred.cpu().numpy(), target.cpu().numpy())` of
-    scripts/train_BCD.py:203-225 without leaving the GPU; read it with `scores()` at the end of an epoch."""
+    task 'bcd' (scripts/train_BCD.py:179-216): labels = (target float (B,1,H,W),); BCEDiceLoss.
+    task 'scd' (scripts/train_SCD.py:205-233): labels = (pre_label, post_label, label_change) int64 (B,H,W); the class
+         labels are masked by label_change, loss = 0.5*(CE0(pre)+CE0(post)) + BCEDice(change) + ChangeSimilarity.
+    task 'bda' (scripts/train_BDA.py:174-204): labels = (label_loc float (B,H,W), label_cls int64 (B,H,W));
+         loss = CE0(cls) + BCEDice(loc).           CE0 = CrossEntropyLoss2d(ignore_index=0).
 
-    def __init__(self, model, lr: float = 2e-4, use_graph: bool = False):
+    The BCEDice kernel also accumulates the confusion matrix hist[target][output > 0.5] of the binary head into
+    `self.cm` (int64 (2,2), device) — the per-step `eval_meter.update_cm(pred.cpu().numpy(), target.cpu().numpy())`
+    of scripts/train_BCD.py:203-225 without leaving the GPU; read it with `scores()` at the end of an epoch.
+    `self.parts` holds the device scalars of the last iteration's loss terms (seg / binary / sim), as the scripts log."""
+
+    def __init__(self, model, lr: float = 2e-4, use_graph: bool = False, task: str = "bcd"):
+        if task not in ("bcd", "scd", "bda"):
+            raise ValueError(f"TrainStep: unknown task {task!r}")
+        self.task = task
         self.model = model.train()
         self.opt = FlatAdam(model, lr=lr)
         self.cm = torch.zeros(2, 2, dtype=torch.int64, device=self.opt.flat_p.device)
+        self.sim = ChangeSimilarity()
+        self.parts = {}
         self.use_graph = use_graph
         self.graph = None
         self.static = None
         self.loss = None
 
-    def _iteration(self, pre, post, target) -> torch.Tensor:
+    def _loss(self, pre, post, labels) -> torch.Tensor:
+        if self.task == "bcd":
+            return bce_dice_loss(self.model.update_bcd(pre, post), labels[0], cm=self.cm)
+        if self.task == "scd":
+            pre_label, post_label, label_change = labels
+            pre_label, post_label = pre_label * label_change, post_label * label_change
+            pre_mask, post_mask, change_mask = self.model.update_scd(pre, post)
+            seg = cross_entropy_2d(pre_mask, pre_label, 0) + cross_entropy_2d(post_mask, post_label, 0)
+            binary = bce_dice_loss(change_mask, label_change.unsqueeze(1).float(), cm=self.cm)
+            sim = self.sim(pre_mask[:, 1:], post_mask[:, 1:], label_change.unsqueeze(1))
+            self.parts = {"seg": seg.detach(), "binary": binary.detach(), "sim": sim.detach()}
+            return seg * 0.5 + binary + sim
+        label_loc, label_cls = labels
+        pred_cls, pred_loc = self.model.update_bda(pre, post)
+        seg = cross_entropy_2d(pred_cls, label_cls, 0)
+        binary = bce_dice_loss(pred_loc, label_loc.unsqueeze(1), cm=self.cm)
+        self.parts = {"seg": seg.detach(), "binary": binary.detach()}
+        return seg + binary
+
+    def _iteration(self, pre, post, *labels) -> torch.Tensor:
         self.opt.zero_grad()
-        out = self.model.update_bcd(pre, post)
-        loss = bce_dice_loss(out, target, cm=self.cm)
+        loss = self._loss(pre, post, labels)
         loss.backward()
         return loss.detach()
 
-    def eager(self, pre: torch.Tensor, post: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None):
+    def eager(self, pre: torch.Tensor, post: torch.Tensor, *labels: torch.Tensor, lr: Optional[float] = None):
         """One iteration without the graph (any batch size — e.g. the ragged last batch of an epoch)."""
-        loss = self._iteration(pre, post, target)
+        loss = self._iteration(pre, post, *labels)
         self.opt.all_reduce()
         self.opt.step(lr)
         return loss
 
-    def __call__(self, pre: torch.Tensor, post: torch.Tensor, target: torch.Tensor, lr: Optional[float] = None):
-        """pre/post (B,3,H,W), target (B,1,H,W) on the GPU.  Returns the (device) loss of this iteration."""
+    def __call__(self, pre: torch.Tensor, post: torch.Tensor, *labels: torch.Tensor, lr: Optional[float] = None):
+        """pre/post (B,3,H,W) and the task's labels on the GPU.  Returns the (device) loss of this iteration."""
         if not self.use_graph:
-            return self.eager(pre, post, target, lr)
+            return self.eager(pre, post, *labels, lr=lr)
         if self.graph is None:
             # warm-up on a side stream (also sets every kernel's shared-memory attribute), then capture
-            self.static = (pre.clone(), post.clone(), target.clone())
+            self.static = tuple(t.clone() for t in (pre, post) + labels)
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -163,7 +193,7 @@ class BCDTrainStep:
                 self.loss = self._iteration(*self.static)
             self.captured_launches = _lib.LAUNCHES[0] - n0 + 1      # + the Adam launch outside the graph
             self.cm.zero_()                                         # drop the warm-up iteration's counts
-        for dst, src in zip(self.static, (pre, post, target)):
+        for dst, src in zip(self.static, (pre, post) + labels):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
@@ -175,3 +205,10 @@ class BCDTrainStep:
         """cm2score of the accumulated training confusion matrix (one small device->host copy)."""
         from .metrics import cm2score
         return cm2score(self.cm.cpu().numpy())
+
+
+class BCDTrainStep(TrainStep):
+    """TrainStep(task='bcd') — the BASELINE.json headline configuration."""
+
+    def __init__(self, model, lr: float = 2e-4, use_graph: bool = False):
+        super().__init__(model, lr=lr, use_graph=use_graph, task="bcd")

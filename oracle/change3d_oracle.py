@@ -411,3 +411,42 @@ def cm_scores(cm) -> dict:
     pre = ((tp + fn) * (tp + fp) + (tn + fp) * (tn + fn)) / (tp + fp + tn + fn) ** 2
     kappa = (oa - pre) / (1 - pre)
     return {'Kappa': kappa, 'IoU': iou, 'F1': f1, 'OA': oa, 'recall': recall, 'precision': precision, 'Pre': pre}
+
+
+def task_loss(task: str, outputs, labels) -> Tensor:
+    """The training loss of each reference script on the model outputs:
+    bcd (scripts/train_BCD.py:200-201)  BCEDice(output, target)
+    scd (scripts/train_SCD.py:215-229)  labels (pre_label, post_label, label_change) int64 (B,H,W), the class labels
+                                        masked by the change map; 0.5*(CE0(pre)+CE0(post)) + BCEDice(change) + Sim
+    bda (scripts/train_BDA.py:181-199)  labels (label_loc float (B,H,W), label_cls int64 (B,H,W)); CE0(cls) + BCEDice(loc)
+    CE0 = CrossEntropyLoss2d(ignore_index=0)."""
+    if task == "bcd":
+        return bce_dice_loss(outputs, labels[0])
+    if task == "scd":
+        pre_mask, post_mask, change_mask = outputs
+        pre_label, post_label, label_change = labels
+        pre_label, post_label = pre_label * label_change, post_label * label_change
+        seg = cross_entropy_2d(pre_mask, pre_label, 0) + cross_entropy_2d(post_mask, post_label, 0)
+        binary = bce_dice_loss(change_mask, label_change.unsqueeze(1).to(change_mask.dtype))
+        sim = change_similarity(pre_mask[:, 1:], post_mask[:, 1:], label_change.unsqueeze(1))
+        return seg * 0.5 + binary + sim
+    if task == "bda":
+        pred_cls, pred_loc = outputs
+        label_loc, label_cls = labels
+        return cross_entropy_2d(pred_cls, label_cls, 0) + bce_dice_loss(pred_loc, label_loc.unsqueeze(1).to(pred_loc.dtype))
+    raise ValueError(task)
+
+
+def synth_labels(task: str, B: int, H: int, W: int, num_class: int, seed: int = 16):
+    """Synthetic labels with the statistics of SURVEY.md §8(d) items 2-4."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    if task == "bcd":
+        return ((torch.rand(B, 1, H, W, generator=g) < 0.05).float(),)
+    if task == "scd":
+        change = (torch.rand(B, H, W, generator=g) < 0.2).long()
+        return (torch.randint(1, num_class, (B, H, W), generator=g), torch.randint(1, num_class, (B, H, W), generator=g),
+                change)
+    if task == "bda":
+        loc = (torch.rand(B, H, W, generator=g) < 0.1).float()
+        return (loc, (loc * torch.randint(1, num_class, (B, H, W), generator=g)).long())
+    raise ValueError(task)

@@ -1,0 +1,99 @@
+"""GPU: the SCD and BDA training iterations (BASELINE.json configs 3-4 at test size) — model.update_scd/bda, the
+scripts' losses on the fused kernels, hand-written backward through three / two decoder heads and T = 5 / 4 frame
+clips — against the oracle in fp64, with torch's own fp32 run of the same oracle as the noise yardstick."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import change3d_oracle as O
+from tests.gpu_util import build_trainer, log, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+KEYS = {
+    "scd": ["decoder_pre.up_c1.0.weight", "decoder_post.up_c4.1.bias", "decoder_change.up_c2.1.weight",
+            "encoder.fc.0.0.weight", "encoder.perception_frames",
+            "encoder.x3d.blocks.1.res_blocks.0.branch2.conv_a.weight",
+            "encoder.x3d.blocks.3.res_blocks.24.branch2.norm_c.weight"],
+    "bda": ["decoder_cls.up_c1.0.weight", "decoder_loc.up_c3.1.weight", "encoder.fc.3.0.weight",
+            "encoder.perception_frames", "encoder.x3d.blocks.2.res_blocks.3.branch2.conv_b.weight",
+            "encoder.x3d.blocks.0.conv.conv_t.weight"],
+}
+
+
+def _case(task, B, H, W, ncls, seed):
+    P = {"scd": 3, "bda": 2}[task]
+    pre, post, _ = O.synth_inputs(B, H, W, seed)
+    labels = O.synth_labels(task, B, H, W, ncls, seed)
+    sd = O.calibrate_running_stats(O.synth_state_dict(O.trainer_schema(task, P, H, W, ncls), seed), task, pre, post)
+    return pre, post, labels, sd
+
+
+def _oracle(task, sd, pre, post, labels, dtype):
+    s = O.clone_sd(sd, dtype=dtype, requires_grad=True)
+    cast = [l.to(dtype) if l.is_floating_point() else l for l in labels]
+    loss = O.task_loss(task, O.trainer_forward(s, task, pre.to(dtype), post.to(dtype), True), cast)
+    loss.backward()
+    return loss.item(), s
+
+
+@pytest.mark.parametrize("task,ncls", [("scd", 7), ("bda", 5)])
+def test_task_loss_and_gradients_vs_oracle(task, ncls):
+    from change3d_b200.train_step import TrainStep
+    B, H, W, seed = 2, 32, 32, 21
+    pre, post, labels, sd = _case(task, B, H, W, ncls, seed)
+    l64, s64 = _oracle(task, sd, pre, post, labels, torch.float64)
+    l32, s32 = _oracle(task, sd, pre, post, labels, torch.float32)
+    model = build_trainer(task, H, W, ncls, sd).train()
+    step = TrainStep(model, task=task)                       # flat gradient buffer + fused losses, eager
+    loss = step._iteration(pre.to(DEV), post.to(DEV), *[l.to(DEV) for l in labels])
+    torch.cuda.synchronize()
+    log(f"{task} train loss: mine {loss.item():.6f} fp64 {l64:.6f} torch-fp32 {l32:.6f}")
+    assert abs(loss.item() - l64) < max(8 * abs(l32 - l64), 1e-4 * abs(l64))
+    flat = {id(p): i for i, p in enumerate(step.opt.params)}
+    named = dict(model.named_parameters())
+    off, offs = 0, []
+    for p in step.opt.params:
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    bad = []
+    for k in KEYS[task]:
+        p = named[k]
+        o = offs[flat[id(p)]]
+        got = step.opt.flat_g[o:o + p.numel()].view(p.shape)
+        t64 = s64[k].grad
+        e_mine, e_ref = rel_err(got, t64), rel_err(s32[k].grad, t64)
+        log(f"{task} grad {k}: |mine-fp64| {e_mine:.3e}  |torch_fp32-fp64| {e_ref:.3e}")
+        if e_mine > max(8.0 * e_ref, 2e-5):
+            bad.append((k, e_mine, e_ref))
+    assert not bad, bad
+    # parameters that the task never reaches stay out of the flat buffers (blocks.4 / blocks.5)
+    assert all(".blocks.4." not in n and ".blocks.5." not in n for n, q in named.items() if id(q) in flat)
+    want_cm = None
+    if task == "scd":
+        with torch.no_grad():
+            out = O.trainer_forward(O.clone_sd(sd), task, pre, post, True)[2]
+        want_cm = O.confusion_matrix(2, labels[2].unsqueeze(1).float().numpy(), (out > 0.5).long().numpy())
+        got_cm = step.cm.cpu().numpy()
+        assert got_cm.sum() == B * H * W and np.abs(got_cm - want_cm).sum() <= 4      # threshold ties at fp32 noise
+
+
+@pytest.mark.parametrize("task,ncls", [("scd", 7), ("bda", 5)])
+def test_task_train_step_eager_and_graph(task, ncls):
+    from change3d_b200.train_step import TrainStep
+    B, H, W, seed = 2, 32, 32, 22
+    pre, post, labels, sd = _case(task, B, H, W, ncls, seed)
+    dl = [l.to(DEV) for l in labels]
+    traj = []
+    for use_graph in (False, True):
+        model = build_trainer(task, H, W, ncls, sd).train()
+        step = TrainStep(model, lr=2e-4, use_graph=use_graph, task=task)
+        ls = [step(pre.to(DEV), post.to(DEV), *dl).item() for _ in range(4)]
+        assert all(np.isfinite(ls)) and ls[-1] < ls[0]
+        assert step.cm.sum().item() == 4 * B * H * W
+        assert set(step.parts) == ({"seg", "binary", "sim"} if task == "scd" else {"seg", "binary"})
+        traj.append(ls)
+    log(f"{task} loss trajectory eager {traj[0]} graph {traj[1]}")
+    assert abs(traj[0][0] - traj[1][0]) < 1e-4 * abs(traj[0][0])
+    assert all(abs(a - b) < 2e-2 * abs(a) for a, b in zip(*traj))

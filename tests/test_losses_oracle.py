@@ -85,3 +85,31 @@ def test_product_losses_refuse_cpu_tensors():
     sc = metrics.cm2score(np.array([[90, 2], [3, 5]]))
     ref = O.cm_scores(np.array([[90, 2], [3, 5]]))
     assert all(abs(sc[k] - ref[k]) < 1e-15 for k in ref)
+
+
+def test_task_loss_matches_reference_loss_functions():
+    """O.task_loss (the per-script loss formulas) against the reference's own loss functions on random heads
+    (authoring container only: needs /root/reference)."""
+    import importlib
+    from oracle import reference_loader as R
+    if not R.available():
+        pytest.skip("reference tree not present")
+    R.load()
+    mu = importlib.import_module("model.utils")
+    gen = torch.Generator().manual_seed(9)
+    B, H, W = 2, 12, 10
+    # scripts/train_SCD.py:215-229
+    pre_m, post_m = torch.randn(B, 7, H, W, generator=gen), torch.randn(B, 7, H, W, generator=gen)
+    chg = torch.sigmoid(torch.randn(B, 1, H, W, generator=gen))
+    labels = O.synth_labels("scd", B, H, W, 7, 9)
+    pl, ql, lc = labels[0] * labels[2], labels[1] * labels[2], labels[2]
+    seg = mu.CrossEntropyLoss2d(ignore_index=0)
+    want = (seg(pre_m, pl) + seg(post_m, ql)) * 0.5 + mu.BCEDiceLoss(chg, lc.unsqueeze(1).float()) \
+        + mu.ChangeSimilarity()(pre_m[:, 1:], post_m[:, 1:], lc.unsqueeze(1))
+    got = O.task_loss("scd", (pre_m, post_m, chg), labels)
+    assert abs(got.item() - want.item()) < 1e-5
+    # scripts/train_BDA.py:181-199
+    cls, loc = torch.randn(B, 5, H, W, generator=gen), torch.sigmoid(torch.randn(B, 1, H, W, generator=gen))
+    l_loc, l_cls = O.synth_labels("bda", B, H, W, 5, 9)
+    want = seg(cls, l_cls) + mu.BCEDiceLoss(loc, l_loc.unsqueeze(1))
+    assert abs(O.task_loss("bda", (cls, loc), (l_loc, l_cls)).item() - want.item()) < 1e-5
