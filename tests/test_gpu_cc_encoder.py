@@ -1,0 +1,53 @@
+"""GPU: change-captioning feature path (Trainer.update_cc -> Encoder.forward(output_final=True), res5 stage:
+192/432 channels, SE reduction 32, 15 blocks) on the sm_100a kernels — forward and backward against the oracle in
+fp64, with the reference's own fp32 result (tests/golden/cc_enc_b2_32.npz) as the noise yardstick."""
+import argparse
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import change3d_oracle as O
+from oracle.make_golden_cc import B, GRAD_KEYS, H, SEED, W, weights
+from tests.gpu_util import log, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_cc_feature_path_forward_backward(golden_dir):
+    from change3d_b200.model.trainer import Encoder
+    g = np.load(os.path.join(golden_dir, "cc_enc_b2_32.npz"))
+    full = O.synth_state_dict(O.trainer_schema("bcd", 1, H, W, 1), SEED)
+    pre, post, _ = O.synth_inputs(B, H, W, SEED)
+    s64 = O.clone_sd(full, dtype=torch.float64, requires_grad=True)
+    o64 = O.encoder_forward(s64, pre.double(), post.double(), 1, True, output_final=True)
+    (o64 * weights(SEED).double()).sum().backward()
+    args = argparse.Namespace(num_perception_frame=1, num_class=1, in_height=H, in_width=W, dataset="LEVIR-CC",
+                              pretrained="/nonexistent/X3D_L.pyth")
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = Encoder(args, [24, 24, 48, 96])
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in full.items() if k.startswith("encoder.")}, strict=True)
+    enc = enc.to(DEV).float().train()
+    out = enc(pre.to(DEV), post.to(DEV), True)
+    assert tuple(out.shape) == (B, 192, H // 16, W // 16)
+    (out * weights(SEED).to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    e_mine, e_ref = rel_err(out, o64), rel_err(g["out"], o64)
+    log(f"cc feature path out: |mine-fp64| {e_mine:.3e}  |reference_fp32-fp64| {e_ref:.3e}")
+    assert e_mine <= max(8 * e_ref, 1e-3)                     # north_star: forward within 1e-3 relative
+    named = dict(enc.named_parameters())
+    bad = []
+    for k in GRAD_KEYS:
+        e_mine, e_ref = rel_err(named[k].grad, s64["encoder." + k].grad), rel_err(g["grad:" + k], s64["encoder." + k].grad)
+        log(f"cc grad {k}: |mine-fp64| {e_mine:.3e}  |reference_fp32-fp64| {e_ref:.3e}")
+        if e_mine > max(8.0 * e_ref, 2e-5):
+            bad.append((k, e_mine, e_ref))
+    assert not bad, bad
+    k = "x3d.blocks.4.res_blocks.14.branch2.norm_c.running_mean"
+    assert rel_err(enc.state_dict()[k], g["stat:" + k]) < 1e-3
+    # parameters the path never reaches (enhance convs, classification head blocks.5) receive no gradient
+    assert all(p.grad is None for n, p in named.items() if n.startswith("fc.") or ".blocks.5." in n)
