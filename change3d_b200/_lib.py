@@ -16,6 +16,8 @@ PRO_NONE, PRO_BN_RELU, PRO_BN_GATE_SWISH, PRO_BNBWD, PRO_ABSDIFF, PRO_MASK_POS =
 MAP_DENSE, MAP_SUB2, MAP_CONVT_FWD, MAP_CONVT_BWD = range(4)
 EPI_STORE, EPI_RELU_ADD, EPI_SWISH_BWD, EPI_ADD2, EPI_CONVT, EPI_ABSDIFF_BWD = range(6)
 
+GEMM_W_CONSTANT = 1     # C3D_GEMM_W_CONSTANT
+
 _fp = C.c_void_p   # device pointers travel as integers
 
 
@@ -33,7 +35,7 @@ class GemmDesc(C.Structure):
                 ("Kred", C.c_int), ("N", C.c_int), ("Ns", C.c_int), ("M", C.c_longlong),
                 ("Y", _fp), ("out_img_stride", C.c_longlong), ("epi", C.c_int), ("stats", _fp),
                 ("E1", _fp), ("e1_img_stride", C.c_longlong), ("E2", _fp), ("ebnp", _fp), ("egate", _fp),
-                ("bias", _fp), ("Y2", _fp), ("rows_per_sample", C.c_longlong)]
+                ("bias", _fp), ("Y2", _fp), ("rows_per_sample", C.c_longlong), ("flags", C.c_int)]
 
 
 class WgradDesc(C.Structure):

@@ -51,6 +51,41 @@ __device__ __forceinline__ float swish_gradf_(float u) {
 
 static inline int c3d_check_last(cudaError_t e) { return e == cudaSuccess ? C3D_OK : C3D_ERR_CUDA; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// Kernels launched through c3d_launch_pdl may become resident while the previous kernel of the stream is still
+// running; everything they do before pdl_wait() must neither read data written earlier in the step nor write
+// global memory.  pdl_wait() returns once every earlier kernel has completed and its writes are visible.
+// pdl_trigger() lets the NEXT kernel's CTAs start being scheduled; it must come after this CTA has acquired
+// everything a co-resident early CTA could take away from it (tensor memory columns).
+// Both are no-ops for a kernel launched without the attribute (the default, see c3d_pdl_enabled).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#include <stdlib.h>
+// Off by default: measured on B200 at batch 32 the step is 2.3 % SLOWER with it (64.19 vs 62.72 ms, same box,
+// profiles/r01_summary.md section 5) -- the early-resident CTAs of the next kernel compete with the weight-gradient
+// GEMMs that already fill the dependency bubbles from the side stream.  C3D_PDL=1 turns it on (read per launch).
+static inline bool c3d_pdl_enabled() {
+  const char* v = getenv("C3D_PDL");
+  return v && atoi(v) != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t c3d_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = c3d_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Operand descriptor for the pointwise-GEMM family (see pw_gemm.cu).
 struct TileSrc {
   const float* A;      // primary tensor

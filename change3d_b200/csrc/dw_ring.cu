@@ -101,6 +101,9 @@ template <int T>
 __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
                                                             const float* __restrict__ w, float* __restrict__ Y,
                                                             double* __restrict__ stats, const Geo G) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   constexpr int SF = T * TS;                          // floats per ring slot
   extern __shared__ __align__(16) float sm[];
   float* ring = sm;                                   // [R][T][PIX][CB]
@@ -280,6 +283,9 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
                                                             const float* __restrict__ bnp_a, const float* __restrict__ w,
                                                             float* __restrict__ DR, float* __restrict__ dW,
                                                             double* __restrict__ stats_a, const Geo G, const FuseArgs F) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   constexpr int SF = T * TS;
   extern __shared__ __align__(16) float sm[];
   float* ring = sm;                                                  // [R][T][PIX][CB]
@@ -521,6 +527,9 @@ template <int T>
 __global__ void __launch_bounds__(NT, 2) dw_fwd_ring2_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
                                                              const float* __restrict__ w, float* __restrict__ Y,
                                                              double* __restrict__ stats, const Geo2 G) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   constexpr int SF = T * TS;
   extern __shared__ __align__(16) float sm[];
   float* ring = sm;                                   // [R][T][PIX][CB] input rows
@@ -678,6 +687,9 @@ __global__ void __launch_bounds__(NT, 1) dw_bwd_ring2_kernel(const float* __rest
                                                              const float* __restrict__ bnp_a, const float* __restrict__ w,
                                                              float* __restrict__ DR, float* __restrict__ dW,
                                                              double* __restrict__ stats_a, const Geo2 G) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   constexpr int SF = T * TS;
   extern __shared__ __align__(16) float sm[];
   float* ring = sm;                                                  // [R][T][PIX][CB] dy rows
@@ -890,17 +902,17 @@ int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, flo
     case 3:
       e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_fwd_ring_kernel<3><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
       break;
     case 4:
       e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_fwd_ring_kernel<4><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
       break;
     default:
       e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return C3D_ERR_SMEM;
-      dwr::dw_fwd_ring_kernel<5><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
       break;
   }
   return c3d_check_last(cudaGetLastError());
@@ -915,12 +927,12 @@ static int launch_bwd(const float* dy, const float* ya, const float* bnp_a, cons
   if (fuse) {
     e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return C3D_ERR_SMEM;
-    dwr::dw_bwd_ring_kernel<T, true><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G, *fuse);
+    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, true>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, *fuse);
   } else {
     dwr::FuseArgs none = {nullptr, nullptr, nullptr, nullptr, nullptr};
     e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return C3D_ERR_SMEM;
-    dwr::dw_bwd_ring_kernel<T, false><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G, none);
+    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, false>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, none);
   }
   return c3d_check_last(cudaGetLastError());
 }
@@ -982,7 +994,7 @@ int c3d_launch_dw_fwd_ring2(const float* X, const float* bnp, const float* w, fl
 #define C3D_LAUNCH_FWD2(TT)                                                                                                 \
   e = cudaFuncSetAttribute(dwr::dw_fwd_ring2_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
   if (e != cudaSuccess) return C3D_ERR_SMEM;                                                                                 \
-  dwr::dw_fwd_ring2_kernel<TT><<<grid, dwr::NT, smem, st>>>(X, bnp, w, Y, stats, G);
+  c3d_launch_pdl(dwr::dw_fwd_ring2_kernel<TT>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
   if (T == 3) { C3D_LAUNCH_FWD2(3) } else if (T == 4) { C3D_LAUNCH_FWD2(4) } else { C3D_LAUNCH_FWD2(5) }
 #undef C3D_LAUNCH_FWD2
   return c3d_check_last(cudaGetLastError());
@@ -1000,7 +1012,7 @@ int c3d_launch_dw_bwd_ring2(const float* dy, const float* ya, const float* bnp_a
 #define C3D_LAUNCH_BWD2(TT)                                                                                                 \
   e = cudaFuncSetAttribute(dwr::dw_bwd_ring2_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
   if (e != cudaSuccess) return C3D_ERR_SMEM;                                                                                 \
-  dwr::dw_bwd_ring2_kernel<TT><<<grid, dwr::NT, smem, st>>>(dy, ya, bnp_a, w, dr, dW, stats_a, G);
+  c3d_launch_pdl(dwr::dw_bwd_ring2_kernel<TT>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G);
   if (T == 3) { C3D_LAUNCH_BWD2(3) } else if (T == 4) { C3D_LAUNCH_BWD2(4) } else { C3D_LAUNCH_BWD2(5) }
 #undef C3D_LAUNCH_BWD2
   return c3d_check_last(cudaGetLastError());

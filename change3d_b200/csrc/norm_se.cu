@@ -35,6 +35,9 @@ __device__ __forceinline__ void bn_params_for_channel(const double* stats, int g
 __global__ void bn_finalize_kernel(const double* stats, int groups, long long count, const float* gamma,
                                    const float* beta, float* rm, float* rv, int C, int Cs, float momentum, float eps,
                                    int training, float* bnp) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
     if (c >= C) {
       bnp[c] = 0.f; bnp[Cs + c] = 0.f; bnp[2 * Cs + c] = 0.f; bnp[3 * Cs + c] = 0.f;
@@ -51,7 +54,7 @@ extern "C" int c3d_bn_finalize(const double* stats, int groups, long long count,
                                int training, float* bnp, void* stream_) {
   if (!gamma || !beta || !bnp || C <= 0 || Cs < C) return C3D_ERR_ARG;
   if (training ? (!stats || groups <= 0 || count <= 0) : (!running_mean || !running_var)) return C3D_ERR_ARG;
-  bn_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(stats, groups, count, gamma, beta, running_mean,
+  c3d_launch_pdl(bn_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, gamma, beta, running_mean,
                                                             running_var, C, Cs, momentum, eps, training, bnp);
   return c3d_check_last(cudaGetLastError());
 }
@@ -61,6 +64,9 @@ __global__ void __launch_bounds__(256) bn_se_finalize_kernel(
     const double* stats, int N, long long cnt, const float* gamma, const float* beta, float* rm, float* rv, int C,
     int Cs, float momentum, float eps, int training, const float* w1, const float* b1, const float* w2,
     const float* b2, int R, float* bnp, float* zhat_mean, float* hidden, float* gate) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   extern __shared__ float sm[];
   float* pooled = sm;          // [Cs]
   float* hid = sm + Cs;        // [R]
@@ -117,7 +123,7 @@ extern "C" int c3d_bn_se_finalize(const double* stats, int N, long long count_pe
   if (!training && (!running_mean || !running_var)) return C3D_ERR_ARG;
   if (w1 && (!b1 || !w2 || !b2 || R <= 0 || !hidden || !gate)) return C3D_ERR_ARG;
   size_t smem = (size_t)(Cs + (R > 0 ? R : 0)) * sizeof(float);
-  bn_se_finalize_kernel<<<N, 256, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, gamma, beta, running_mean,
+  c3d_launch_pdl(bn_se_finalize_kernel, dim3(N), dim3(256), smem, (cudaStream_t)stream_, stats, N, count_per_sample, gamma, beta, running_mean,
                                                                  running_var, C, Cs, momentum, eps, training, w1, b1,
                                                                  w2, b2, R, bnp, zhat_mean, hidden, gate);
   return c3d_check_last(cudaGetLastError());
@@ -126,6 +132,9 @@ extern "C" int c3d_bn_se_finalize(const double* stats, int N, long long count_pe
 __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restrict__ A, const float* __restrict__ bnpA,
                                                           const float* __restrict__ B, const float* __restrict__ bnpB,
                                                           float* __restrict__ Y, long long total4, int Cs) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   const int q4 = Cs >> 2;
   // channel quad of element i tracked incrementally (a 64-bit modulo per element costs more than the arithmetic)
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -151,7 +160,7 @@ extern "C" int c3d_bn_add_relu(const float* A, const float* bnpA, const float* B
   const long long total4 = M * (Cs >> 2);
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_add_relu_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(A, bnpA, B, bnpB, Y, total4, Cs);
+  c3d_launch_pdl(bn_add_relu_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, A, bnpA, B, bnpB, Y, total4, Cs);
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -168,6 +177,9 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
     const float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ yc,
     const float* __restrict__ bnp_c, const float* __restrict__ y1, const float* __restrict__ bnp_1,
     float* __restrict__ d_pre, double* __restrict__ stats_c, double* __restrict__ stats_1, long long M, int Cs) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   extern __shared__ float sm[];   // [3][Cs]
   for (int i = threadIdx.x; i < 3 * Cs; i += 256) sm[i] = 0.f;
   __syncthreads();
@@ -222,7 +234,7 @@ extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const flo
   const int rpb = 256 / (Cs >> 2);
   long long blocks = (M + rpb - 1) / rpb;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  relu_bwd_stats_kernel<<<(unsigned)blocks, 256, 3 * Cs * sizeof(float), (cudaStream_t)stream_>>>(
+  c3d_launch_pdl(relu_bwd_stats_kernel, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_, 
       dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
   return c3d_check_last(cudaGetLastError());
 }
@@ -230,6 +242,9 @@ extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const flo
 // stats = double[groups][2][Cs] (sum d, sum d*yhat) -> coef[2][Cs] = (mean d, mean d*yhat); dgamma, dbeta
 __global__ void bn_bwd_finalize_kernel(const double* stats, int groups, long long count, int C, int Cs, float* coef,
                                        float* dgamma, float* dbeta) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
     double s = 0.0, t = 0.0;
     if (c < C)
@@ -243,7 +258,7 @@ __global__ void bn_bwd_finalize_kernel(const double* stats, int groups, long lon
 extern "C" int c3d_bn_bwd_finalize(const double* stats, int groups, long long count, int C, int Cs, float* coef,
                                    float* dgamma, float* dbeta, void* stream_) {
   if (!stats || !coef || !dgamma || !dbeta || groups <= 0 || count <= 0 || C <= 0 || Cs < C) return C3D_ERR_ARG;
-  bn_bwd_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(stats, groups, count, C, Cs, coef, dgamma, dbeta);
+  c3d_launch_pdl(bn_bwd_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, C, Cs, coef, dgamma, dbeta);
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -254,6 +269,9 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     const float* __restrict__ zhat_mean, const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cs, int R,
     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dpool,
     float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
+  pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
+  pdl_wait();      // then wait for the earlier kernels whose results this one reads
+
   extern __shared__ float sm[];
   float* dps = sm;               // [N][C]   grad wrt pre-sigmoid
   float* dpr = sm + (size_t)N * C;   // [N][R]   grad wrt pre-relu
@@ -339,7 +357,7 @@ extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long coun
   size_t smem = gate ? ((size_t)N * C + (size_t)N * R) * sizeof(float) : 0;
   if (smem > 200 * 1024) return C3D_ERR_SMEM;
   cudaFuncSetAttribute(se_bn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  se_bn_bwd_finalize_kernel<<<1, 1024, smem, (cudaStream_t)stream_>>>(stats, N, count_per_sample, bnp, gamma, beta, gate,
+  c3d_launch_pdl(se_bn_bwd_finalize_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream_, stats, N, count_per_sample, bnp, gamma, beta, gate,
                                                                     hidden, zhat_mean, w1, w2, C, Cs, R, coef, dgamma,
                                                                     dbeta, dpool, dw1, db1, dw2, db2);
   return c3d_check_last(cudaGetLastError());

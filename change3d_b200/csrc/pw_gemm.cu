@@ -363,6 +363,7 @@ extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   g.E1 = d->E1; g.e1_img_stride = d->e1_img_stride; g.E2 = d->E2;
   g.ebnp = d->ebnp; g.egate = d->egate; g.bias = d->bias; g.Y2 = d->Y2;
   g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : (1LL << 62);
+  g.w_const = (d->flags & C3D_GEMM_W_CONSTANT) ? 1 : 0;
   const int ncls = d->epi == EPI_CONVT ? 4 : 1;
   if (env_flag("C3D_TC", 1)) {
     g.NB = 0; g.nsplit = 1;

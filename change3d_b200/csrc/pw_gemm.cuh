@@ -18,6 +18,7 @@ struct GemmArgs {
   long long rows_per_sample;
   int NB;        // columns handled per CTA (multiple of 64)
   int nsplit;    // grid.y = ncls * nsplit
+  int w_const;   // C3D_GEMM_W_CONSTANT: W may be read before pdl_wait()
 };
 
 struct RowMeta {       // per tile row, in shared memory

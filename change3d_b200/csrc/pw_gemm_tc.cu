@@ -237,6 +237,9 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+  // Programmatic dependent launch: everything up to here touches no global memory.  Model parameters are constant
+  // within a step, so their staging below may also overlap the previous kernel's tail; other weights wait first.
+  if (!g.w_const) pdl_wait();
   // resident weights, split and laid out for UMMA (zero outside the logical matrix)
   {
     const int kq4 = K >> 2;
@@ -264,6 +267,8 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const long long d_t1 = dbg_on ? clock64() : 0;
+  pdl_trigger();     // tensor memory is allocated: the next kernel's CTAs may start their own setup
+  pdl_wait();        // operands, BN blocks, statistics: produced by earlier kernels
 
   const long long ntiles = (g.M + BM - 1) / BM;
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -814,8 +819,8 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
     }
     return c3d_check_last(cudaGetLastError());
   }
-  tc::pw_gemm_tc_kernel<NEPI, NPROD, WPS, CPS><<<grid, (NEPI + 1 + NPROD) * 32, smem, stream>>>(P, tmA, tmA2);
-  return c3d_check_last(cudaGetLastError());
+  return c3d_check_last(c3d_launch_pdl(tc::pw_gemm_tc_kernel<NEPI, NPROD, WPS, CPS>, grid, dim3((NEPI + 1 + NPROD) * 32), smem,
+                                       stream, P, tmA, tmA2));
 }
 
 // Host-side eligibility + launch.  Returns -1 when the shape / mode is not handled here (caller falls back

@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const long long d_t1 = dbg_on ? clock64() : 0;
+  pdl_trigger();     // programmatic dependent launch: setup done (tensor memory allocated), operands need the
+  pdl_wait();        // earlier kernels' results
 
   const long long ntiles = (P.M + P.PT - 1) / P.PT;
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -410,6 +412,6 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
     }
     return c3d_check_last(cudaGetLastError());
   }
-  tcm::pw_wgrad_mn_kernel<<<(unsigned)gx, tcm::NTHREADS, smem, stream>>>(P, tmB, tmB2, tmS, tmS2);
-  return c3d_check_last(cudaGetLastError());
+  return c3d_check_last(c3d_launch_pdl(tcm::pw_wgrad_mn_kernel, dim3((unsigned)gx), dim3(tcm::NTHREADS), smem, stream, P, tmB,
+                                       tmB2, tmS, tmS2));
 }

@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const Params P
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long d_t1 = dbg_on ? clock64() : 0;
+  pdl_trigger();     // programmatic dependent launch: setup done (tensor memory allocated), operands need the
+  pdl_wait();        // earlier kernels' results
 
   const long long ntiles = (P.M + PT - 1) / PT;
   const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -357,6 +359,5 @@ int c3d_launch_pw_wgrad_tc(const TileSrc& p, const TileSrc& q, long long M, floa
     }
     return c3d_check_last(cudaGetLastError());
   }
-  tcw::pw_wgrad_tc_kernel<<<(unsigned)gx, tcw::NTHREADS, smem, stream>>>(P);
-  return c3d_check_last(cudaGetLastError());
+  return c3d_check_last(c3d_launch_pdl(tcw::pw_wgrad_tc_kernel, dim3((unsigned)gx), dim3(tcw::NTHREADS), smem, stream, P));
 }

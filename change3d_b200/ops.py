@@ -96,6 +96,8 @@ def pw_gemm(a: L.Operand, W: torch.Tensor, *, w_sr: int, w_so: int, Kred: int, N
     d.E1 = _ptr(E1); d.e1_img_stride = e1_img_stride; d.E2 = _ptr(E2)
     d.ebnp = _ptr(ebnp); d.egate = _ptr(egate); d.bias = _ptr(bias); d.Y2 = _ptr(Y2)
     d.rows_per_sample = rows_per_sample
+    # module parameters are constant within a step; derived weight tensors (re-laid-out copies) are not
+    d.flags = L.GEMM_W_CONSTANT if isinstance(W, torch.nn.Parameter) else 0
     ka = a.ld * (a.nseg if a.nseg else (4 if a.map == MAP_CONVT_FWD else 16 if a.map == MAP_CONVT_BWD else 1))
     nbytes = 4 * (M * ka * (2 if a.A2 else 1) + M * Ns * (1 + (1 if E1 is not None else 0)) + Kred * N)
     with _Timed("pw_gemm", nbytes):

@@ -79,7 +79,13 @@ typedef struct c3d_gemm_desc {
   const float* bias;
   float* Y2;
   long long rows_per_sample;  /* epi 2: rows per batch sample */
+  int flags;                  /* C3D_GEMM_* */
 } c3d_gemm_desc;
+
+/* W is a model parameter: no kernel earlier in this training / inference step writes it, so the launch may
+ * stage it ahead of stream order (programmatic dependent launch, overlapping the previous kernel's tail).
+ * Leave it clear for weights produced on the stream (re-laid-out copies, freshly loaded checkpoints ...). */
+#define C3D_GEMM_W_CONSTANT 1
 
 int c3d_pw_gemm(const c3d_gemm_desc* desc, void* cuda_stream);
 

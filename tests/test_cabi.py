@@ -45,9 +45,9 @@ def test_ctypes_structs_match_c_layout():
 #include <stddef.h>
 #include "change3d_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(c3d_operand), sizeof(c3d_gemm_desc), sizeof(c3d_wgrad_desc),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(c3d_operand), sizeof(c3d_gemm_desc), sizeof(c3d_wgrad_desc),
          offsetof(c3d_operand, img_stride), offsetof(c3d_operand, seg0), offsetof(c3d_gemm_desc, W),
-         offsetof(c3d_gemm_desc, rows_per_sample), offsetof(c3d_wgrad_desc, dW));
+         offsetof(c3d_gemm_desc, rows_per_sample), offsetof(c3d_wgrad_desc, dW), offsetof(c3d_gemm_desc, flags));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -57,7 +57,7 @@ int main(void) {
         got = [int(v) for v in subprocess.check_output([exe]).split()]
     want = [C.sizeof(_lib.Operand), C.sizeof(_lib.GemmDesc), C.sizeof(_lib.WgradDesc),
             _lib.Operand.img_stride.offset, _lib.Operand.seg0.offset, _lib.GemmDesc.W.offset,
-            _lib.GemmDesc.rows_per_sample.offset, _lib.WgradDesc.dW.offset]
+            _lib.GemmDesc.rows_per_sample.offset, _lib.WgradDesc.dW.offset, _lib.GemmDesc.flags.offset]
     assert got == want
 
 

@@ -215,3 +215,26 @@ def test_train_step_confusion_matrix_eager_and_graph():
     assert np.array_equal(cm_e[0], cm_g[0])                    # first step: identical weights, identical mask
     assert abs(l_e[0] - l_g[0]) < 1e-5 and all(abs(a - b) < 5e-3 for a, b in zip(l_e, l_g))
     assert l_e[-1] < l_e[0]
+
+
+def test_train_step_with_programmatic_dependent_launch():
+    """C3D_PDL=1 (optional, off by default because it measured slower): same first-step loss and confusion matrix
+    as the default launch path, finite decreasing losses afterwards."""
+    from change3d_b200.train_step import BCDTrainStep
+    from tests.gpu_util import build_trainer
+    B, H, W = 2, 64, 64
+    pre, post, target = (t.to(DEV) for t in O.synth_inputs(B, H, W, 11))
+    runs = {}
+    for pdl in ("0", "1"):
+        os.environ["C3D_PDL"] = pdl
+        try:
+            torch.manual_seed(16)
+            step = BCDTrainStep(build_trainer("bcd", H, W, 1).train(), lr=2e-4, use_graph=(pdl == "1"))
+            ls = [step(pre, post, target).item() for _ in range(4)]
+            runs[pdl] = (ls, step.cm.cpu().numpy().copy())
+        finally:
+            os.environ.pop("C3D_PDL", None)
+    log("PDL off " + " ".join(f"{v:.5f}" for v in runs["0"][0]) + " | on " + " ".join(f"{v:.5f}" for v in runs["1"][0]))
+    assert abs(runs["0"][0][0] - runs["1"][0][0]) < 1e-5
+    assert all(abs(a - b) < 5e-3 for a, b in zip(runs["0"][0], runs["1"][0]))
+    assert runs["1"][0][-1] < runs["1"][0][0] and runs["1"][1].sum() == 4 * B * H * W
