@@ -132,11 +132,11 @@ extern "C" int c3d_stem_fwd(const float* const* frame_ptr, const long long* stri
 //   dwt[c][tap]        += dy[t][c] * s[t+tap-2][c]            (s = spatial conv output, recomputed)
 //   dwxy[c][ci,kh,kw]  += ds[f][h,w,c] * in[f][ci][h+kh-1][w+kw-1]
 //   dperc[ci][f-1][h][w] += sum_{c,kh,kw} wxy[c][ci,kh,kw] * ds[f][h-kh+1][w-kw+1][c]   (frames 1..P only)
-// One persistent CTA walks 32x8 pixel tiles; ds for tile+halo lives in shared memory.
+// Persistent CTAs walk BTW x BTH pixel tiles; ds for tile+halo lives in shared memory.
 // ------------------------------------------------------------------------------------------------
 #define STEM_DSLD 28   // padded pixel stride of the ds tile (bank-conflict-free float4 reads)
 
-template <int T>
+template <int T, int BTW, int BTH>
 __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, const float* __restrict__ dpre,
                                                        const float* __restrict__ ys, const float* __restrict__ bnp,
                                                        const float* __restrict__ coef, const float* __restrict__ wxy,
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
                                                        float* __restrict__ dwt, float* __restrict__ dperc, int B, int H,
                                                        int W) {
   constexpr int P = T - 2;
-  constexpr int PW = STEM_TW + 2, PH = STEM_TH + 2, NPIX = PW * PH;
+  constexpr int PW = BTW + 2, PH = BTH + 2, NPIX = PW * PH;
   extern __shared__ __align__(16) float sm[];
   float* patch = sm;                                   // [T][3][PH][PW]
   float* ds = patch + T * 3 * NPIX;                    // [T][NPIX][STEM_DSLD]
@@ -169,12 +169,12 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
   const int b_ci = tb / 9, b_kh = (tb % 9) / 3, b_kw = tb % 3;
   float4 dwxy_acc = f4zero();
 
-  const int tiles_x = (W + STEM_TW - 1) / STEM_TW, tiles_y = (H + STEM_TH - 1) / STEM_TH;
+  const int tiles_x = (W + BTW - 1) / BTW, tiles_y = (H + BTH - 1) / BTH;
   const int ntiles = tiles_x * tiles_y * B;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int n = tile / (tiles_x * tiles_y);
     const int trem = tile - n * tiles_x * tiles_y;
-    const int h0 = (trem / tiles_x) * STEM_TH, w0 = (trem % tiles_x) * STEM_TW;
+    const int h0 = (trem / tiles_x) * BTH, w0 = (trem % tiles_x) * BTW;
     __syncthreads();
     for (int i = tid; i < T * 3 * NPIX; i += 256) {
       int x = i % PW, y = (i / PW) % PH, ci = (i / NPIX) % 3, f = i / (NPIX * 3);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
           *reinterpret_cast<float4*>(ds + (f * NPIX + p) * STEM_DSLD + ca) = o;
         }
         // temporal weight gradient needs s = spatial conv output at interior (non-halo, in-image) pixels
-        const bool interior = inimg && y >= 1 && y <= STEM_TH && x >= 1 && x <= STEM_TW;
+        const bool interior = inimg && y >= 1 && y <= BTH && x >= 1 && x <= BTW;
         if (interior) {
           float4 s[T];
 #pragma unroll
@@ -252,9 +252,9 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
       for (int f = 0; f < T; ++f) {
         const float* pp = patch + (f * 3 + b_ci) * NPIX;
         const float* dp = ds + f * NPIX * STEM_DSLD + 4 * qb;
-        for (int y = 1; y <= STEM_TH; ++y) {
+        for (int y = 1; y <= BTH; ++y) {
 #pragma unroll 4
-          for (int x = 1; x <= STEM_TW; ++x) {
+          for (int x = 1; x <= BTW; ++x) {
             const float xv = pp[(y - 1 + b_kh) * PW + (x - 1 + b_kw)];
             const float4 d = *reinterpret_cast<const float4*>(dp + (y * PW + x) * STEM_DSLD);
             dwxy_acc.x = fmaf(xv, d.x, dwxy_acc.x); dwxy_acc.y = fmaf(xv, d.y, dwxy_acc.y);
@@ -265,9 +265,9 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
     }
     // role C: gradient of the perception frames, one thread per interior pixel
     if (dperc) {
-      const int lx = tid & (STEM_TW - 1), ly = tid / STEM_TW;
+      const int lx = tid & (BTW - 1), ly = tid / BTW;
       const int h = h0 + ly, w = w0 + lx;
-      if (h < H && w < W) {
+      if (ly < BTH && h < H && w < W) {
 #pragma unroll
         for (int f = 1; f <= P; ++f) {
           float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -313,22 +313,36 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
   for (int i = tid; i < 5 * STEM_C; i += 256) { int k = i / STEM_C, c = i - k * STEM_C; atomicAdd(dwt + c * 5 + k, s_dwt[i]); }
 }
 
-template <int T>
-static int launch_stem_bwd(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
-                           const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
-                           cudaStream_t st) {
-  constexpr int NPIX = (STEM_TW + 2) * (STEM_TH + 2);
+template <int T, int BTW, int BTH>
+static int launch_stem_bwd_tile(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
+                                const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
+                                cudaStream_t st) {
+  static_assert(BTW * BTH <= 256 && (BTW & (BTW - 1)) == 0, "one thread per interior pixel in the perception-frame pass");
+  constexpr int NPIX = (BTW + 2) * (BTH + 2);
   const size_t smem = (size_t)(T * 3 * NPIX + T * NPIX * STEM_DSLD + 27 * STEM_C * 2 + 5 * STEM_C * 2) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(stem_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(stem_bwd_kernel<T, BTW, BTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return C3D_ERR_SMEM;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int ntiles = ((W + STEM_TW - 1) / STEM_TW) * ((H + STEM_TH - 1) / STEM_TH) * B;
-  const int per_sm = smem > 110 * 1024 ? 1 : 2;
+  const int ntiles = ((W + BTW - 1) / BTW) * ((H + BTH - 1) / BTH) * B;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));          // co-resident CTAs hide each other's phase barriers
+  per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;           // 127 registers x 256 threads: two CTAs per SM
   int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
-  stem_bwd_kernel<T><<<grid, 256, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W);
+  stem_bwd_kernel<T, BTW, BTH><<<grid, 256, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W);
   return c3d_check_last(cudaGetLastError());
+}
+
+// Tile = 16 x 8 pixels (73 KB of shared memory at T = 3: two CTAs per SM); C3D_STEM_BWD_TILE=32 selects the
+// 32 x 8 tile (133 KB, one CTA per SM) the kernel was first written for.
+template <int T>
+static int launch_stem_bwd(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
+                           const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
+                           cudaStream_t st) {
+  const char* v = getenv("C3D_STEM_BWD_TILE");
+  if (v && atoi(v) == 32)
+    return launch_stem_bwd_tile<T, 32, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
+  return launch_stem_bwd_tile<T, 16, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
 }
 
 extern "C" int c3d_stem_bwd(const float* const* frame_ptr, const long long* stride_n, const long long* stride_c,
