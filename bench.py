@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a captured CUDA graph")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--e2e-mode", default="prefetch", choices=["plain", "prefetch", "both"],
+                    help="how the e2e loop stages its pinned host inputs (both: measure both, report the better)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     return ap.parse_args()
@@ -215,23 +217,42 @@ def run_ours(args):
     else:
         launches_per_step = getattr(step, "captured_launches", None)
 
-    # ---- e2e: public API with pinned host buffers, H2D + step + D2H of the loss in the timed region ----
+    # ---- e2e: public API with pinned host buffers; every step's H2D copy + the step + the D2H read of its loss are
+    # inside the timed region.  --e2e-mode plain: copies on the compute stream right before the step (what the
+    # reference loop does); prefetch: through the package's DevicePrefetcher (copy stream, one batch ahead).
+    from change3d_b200.input_pipeline import DevicePrefetcher
+    k2 = max(3, args.steps)
+
+    def host_batches(n):
+        for _ in range(n):
+            yield (h_pre, h_post, h_tgt)
+
+    def e2e_plain(n):
+        for _ in range(n):
+            d_pre.copy_(h_pre, non_blocking=True); d_post.copy_(h_post, non_blocking=True); d_tgt.copy_(h_tgt, non_blocking=True)
+            float(step(d_pre, d_post, d_tgt).item())
+
+    def e2e_prefetch(n):
+        pf = DevicePrefetcher(host_batches(n), dev)
+        for a_, b_, c_ in pf:
+            float(step(a_, b_, c_).item())
+        assert pf.bytes_staged == n * (h_pre.numel() + h_post.numel() + h_tgt.numel()) * 4
+
     d_pre, d_post, d_tgt = torch.empty_like(pre), torch.empty_like(post), torch.empty_like(tgt)
-    for _ in range(2):
-        d_pre.copy_(h_pre, non_blocking=True); d_post.copy_(h_post, non_blocking=True); d_tgt.copy_(h_tgt, non_blocking=True)
-        float(step(d_pre, d_post, d_tgt).item())
-    barrier()
-    k2 = max(3, args.steps // 2)
-    t0 = time.perf_counter()
-    for _ in range(k2):
-        d_pre.copy_(h_pre, non_blocking=True); d_post.copy_(h_post, non_blocking=True); d_tgt.copy_(h_tgt, non_blocking=True)
-        float(step(d_pre, d_post, d_tgt).item())
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * k2 / float(te.item())
+    e2e_runs = {}
+    for mode in (("plain", "prefetch") if args.e2e_mode == "both" else (args.e2e_mode,)):
+        fn = e2e_plain if mode == "plain" else e2e_prefetch
+        fn(2)
+        barrier()
+        t0 = time.perf_counter()
+        fn(k2)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_runs[mode] = world * B * k2 / float(te.item())
+    e2e_mode = args.e2e_mode if args.e2e_mode != "both" else max(e2e_runs, key=e2e_runs.get)
+    e2e_value = e2e_runs[e2e_mode]
     h2d = (h_pre.numel() + h_post.numel() + h_tgt.numel()) * 4
     # training confusion matrix hist[target][output > 0.5], accumulated on the device by the loss kernel over every
     # step since the graph was captured (the reference copies a 16.8 MB mask to the host per step for this); one
@@ -311,7 +332,8 @@ def run_ours(args):
                            "cuda_graph": not args.no_graph, "wgrad_side_stream": os.environ.get("C3D_SIDE_STREAM", "1") == "1",
                            "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed"},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "steps": k2},
+                        "steps": k2, "input_staging": e2e_mode,
+                        "all_modes": {k: round(v, 2) for k, v in e2e_runs.items()}},
                 "gpu_launches": launches_per_step, "loss": round(loss_val, 5), "clocks": sampler.summary(),
                 "metrics_on_device": {"confusion_matrix": cm_host, "pixels": int(sum(map(sum, cm_host))),
                                       "note": "hist[target][output > 0.5] accumulated by the loss kernel, no per-step D2H"}}

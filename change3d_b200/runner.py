@@ -10,6 +10,8 @@ What differs is where the work happens:
     training set, one NCCL all-reduce of the flat gradient buffer per step (train_step.FlatAdam); rank 0 logs,
     validates and writes checkpoints; no hard-coded `.cuda()` / `CUDA_VISIBLE_DEVICES` (`--gpu_id` is honoured
     only when not launched by torchrun);
+  * batches are staged by `input_pipeline.DevicePrefetcher` (pinned memory, copy stream, one batch ahead) instead of
+    synchronous `.cuda()` calls on the compute stream;
   * the step is the CUDA-graph-captured `BCDTrainStep`; loss and the 2x2 confusion matrix stay on the device
     (losses.bce_dice_loss(cm=...)) and are read back when something is printed (every 5 iterations, like the
     reference's print cadence) and at the end of the epoch — not `loss.item()` + a 16.8 MB mask copy per step.
@@ -29,6 +31,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from .input_pipeline import DevicePrefetcher
 from .losses import bce_dice_loss
 from .metrics import cm2score
 from .model.trainer import Trainer
@@ -107,11 +110,11 @@ def make_loaders(args, world: int, rank: int, datasets=None):
     return train_loader, val_loader, test_loader, len(train_loader)
 
 
-def _to_device(batch, dev):
+def _split(batch):
+    """(img (B,6,H,W), target) already on the device -> pre, post, target as the scripts slice them
+    (scripts/train_BCD.py:182-185), contiguous fp32."""
     img, target = batch
-    pre = img[:, 0:3].to(dev, non_blocking=True).float()
-    post = img[:, 3:6].to(dev, non_blocking=True).float()
-    return pre.contiguous(), post.contiguous(), target.to(dev, non_blocking=True).float()
+    return img[:, 0:3].float().contiguous(), img[:, 3:6].float().contiguous(), target.float()
 
 
 @torch.no_grad()
@@ -122,8 +125,8 @@ def val(args, val_loader, model, epoch, dev):
     cm = torch.zeros(2, 2, dtype=torch.int64, device=dev)
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
     n = 0
-    for batch in val_loader:
-        pre, post, target = _to_device(batch, dev)
+    for batch in DevicePrefetcher(val_loader, dev):          # pinned batches staged one ahead on a copy stream
+        pre, post, target = _split(batch)
         output = model.update_bcd(pre, post)
         loss_sum += bce_dice_loss(output, target, cm=cm)
         n += 1
@@ -140,8 +143,8 @@ def train(args, train_loader, step: BCDTrainStep, epoch: int, max_batches: int, 
     lr = args.lr
     n = 0
     t_epoch = time.time()
-    for iter_idx, batch in enumerate(train_loader):
-        pre, post, target = _to_device(batch, dev)
+    for iter_idx, batch in enumerate(DevicePrefetcher(train_loader, dev)):
+        pre, post, target = _split(batch)
         lr = adjust_learning_rate(args, step.opt, epoch, iter_idx + cur_iter, max_batches, lr_factor=lr_factor)
         if pre.shape[0] != full and step.use_graph:
             # ragged last batch (drop_last=False in the reference): static-shape graph does not apply
