@@ -4,7 +4,6 @@ by the reference's own Encoder (oracle/make_golden_cc.py)."""
 import os
 
 import numpy as np
-import torch
 
 from oracle import change3d_oracle as O
 from oracle.make_golden_cc import B, GRAD_KEYS, H, SEED, W, weights
