@@ -190,3 +190,49 @@ def test_round_helpers_and_depths():
     assert len(net.blocks) == 6
     assert [len(net.blocks[i].res_blocks) for i in range(1, 5)] == [5, 10, 25, 15]
     assert sum(p.numel() for p in net.parameters()) == 6_153_384
+
+
+def test_flat_adam_param_groups_state_dict_and_task_views():
+    """FlatAdam looks like torch's Adam to `adjust_learning_rate` (param_groups), round-trips its state for the
+    reference's checkpoint dict, and installs gradient views for every decoder head of the SCD / BDA models."""
+    from argparse import Namespace
+    from change3d_b200.model.utils import adjust_learning_rate
+    from change3d_b200.train_step import FlatAdam
+    m = _trainer("scd", 32, 32, 7)
+    opt = FlatAdam(m, lr=2e-4)
+    args = Namespace(lr=2e-4, lr_mode="poly", max_epochs=3, step_loss=100)
+    lr = adjust_learning_rate(args, opt, 0, 10, 50)
+    assert opt.param_groups[0]["lr"] == lr and abs(lr - (2e-4 * 0.9 * 11 / 200 + 0.1 * 2e-4)) < 1e-12
+    for name in ("decoder_pre", "decoder_post", "decoder_change"):
+        dec = getattr(m, name)
+        assert len(dec._c3d_grad_views) == len(dec.param_list()) == 10
+        assert all(v.shape == p.shape for v, p in zip(dec._c3d_grad_views, dec.param_list()))
+    opt.step_count = 7
+    opt.m.fill_(0.5)
+    sd = opt.state_dict()
+    assert sd["state"]["step"] == 7 and sd["param_groups"][0]["lr"] == lr and sd["param_groups"][0]["betas"] == (0.9, 0.99)
+    opt2 = FlatAdam(_trainer("scd", 32, 32, 7))
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 7 and torch.equal(opt2.m, opt.m) and opt2.param_groups[0]["lr"] == lr
+    with pytest.raises(ValueError):
+        from change3d_b200.train_step import TrainStep
+        TrainStep(m, task="cc")
+
+
+def test_launch_summary_tool_reproduces_the_committed_traffic_table():
+    """profiles/tools/launch_summary.py on the committed end-of-round ncu launch list: one step = 752 launches, and the
+    per-family DRAM traffic equals profiles/r01b_traffic.json (what bench.py reports as roofline.traffic)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r01b_launches_final.csv")
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "tools", "launch_summary.py"), csv_path,
+                          "--one-step", "--json", os.path.join(str(os.environ.get("TMPDIR", "/tmp")), "c3d_traffic.json")],
+                         capture_output=True, text=True, check=True).stdout
+    assert "period = 752 launches per step" in out
+    got = json.load(open(os.path.join(str(os.environ.get("TMPDIR", "/tmp")), "c3d_traffic.json")))["families"]
+    want = json.load(open(os.path.join(root, "profiles", "r01b_traffic.json")))["families"]
+    assert got == want
+    assert want["pw_gemm"]["launches"] == 190 and 295e6 < want["pw_gemm"]["dram_bytes_per_launch"] < 330e6
