@@ -36,11 +36,14 @@ def main() -> None:
     ap.add_argument("csv")
     ap.add_argument("--json")
     ap.add_argument("--md", action="store_true")
+    ap.add_argument("--by-shape", metavar="REGEX",
+                    help="also list the launches whose kernel name matches REGEX grouped by (kernel, grid, DRAM MB)")
     ap.add_argument("--one-step", action="store_true",
                     help="the launch sequence of a training loop is periodic: keep exactly one period (one step)")
     a = ap.parse_args()
     rows = defaultdict(dict)
     names = {}
+    grids = {}
     with open(a.csv) as f:
         lines = [ln for ln in f if ln.startswith('"')]
     for r in csv.DictReader(lines):
@@ -48,6 +51,7 @@ def main() -> None:
             ({"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r["Metric Unit"], 1.0) if "time" in r["Metric Name"] else
              {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0))
         names[r["ID"]] = r["Kernel Name"]
+        grids[r["ID"]] = r["Grid Size"]
     if a.one_step:
         ids = sorted(rows, key=int)
         seq = [names[i] for i in ids]
@@ -76,6 +80,20 @@ def main() -> None:
                 print(f"| {100 * t / total:.1f} % | {t:.2f} | {n} | {b / 1e9:.1f} | {gbs:.0f} | `{k}` |")
             else:
                 print(f"{100 * t / total:5.1f}%  {t:8.2f} ms  {n:4d}  {b / 1e9:7.2f} GB  {gbs:6.0f} GB/s  {k}")
+    if a.by_shape:
+        shapes = defaultdict(lambda: [0, 0.0, 0.0])
+        for i, m in rows.items():
+            if not re.search(a.by_shape, names[i]):
+                continue
+            b = m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
+            step_mb = 1 if b < 50e6 else 5
+            key = (short(names[i]).replace("void ", ""), grids[i], round(b / 1e6 / step_mb) * step_mb)
+            shapes[key][0] += 1
+            shapes[key][1] += m.get("gpu__time_duration.sum", 0.0)
+            shapes[key][2] += b
+        print("| kernel | grid | DRAM MB / launch | launches | us / launch | DRAM GB/s | ms / step |\n|---|---|---|---|---|---|---|")
+        for (k, grid, _), (n, t, b) in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:30]:
+            print(f"| `{k}` | {grid} | {b / n / 1e6:.0f} | {n} | {1e3 * t / n:.0f} | {b / (t * 1e-3) / 1e9:.0f} | {t:.2f} |")
     if a.json:
         fams = {k: {"launches": n, "time_ms": round(t, 3), "dram_bytes": int(b), "dram_bytes_per_launch": int(b / n)}
                 for k, (n, t, b) in per_family.items() if k != "torch / other"}
