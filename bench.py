@@ -6,8 +6,9 @@ synthetic LEVIR-shape 256x256, batch 32 per GPU (BASELINE.json configs[1]).
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle) on host cores
 
 Prints ONE JSON line on rank 0.  `value` = whole-job pairs/s with the inputs resident in HBM; `e2e` = the same
-step through the public API (change3d_b200.train_step.BCDTrainStep) with pinned HOST inputs, H2D copy and a D2H
-read of the loss inside the timed region.  `roofline` describes the kernel family that takes the most device
+step through the public API (change3d_b200.input_pipeline.DevicePrefetcher feeding change3d_b200.train_step.BCDTrainStep)
+with pinned HOST inputs: every step's H2D copy (on a copy stream, one batch ahead) and a D2H read of its loss are inside
+the timed region (--e2e-mode plain: copies on the compute stream; both: measure both).  `roofline` describes the kernel family that takes the most device
 time, from CUDA events recorded around every launch of a separate profiled step; `cpu_baseline` times the
 oracle (a port of the reference algorithm, oracle/change3d_oracle.py) on this box's host cores.
 """
