@@ -17,6 +17,8 @@
 extern "C" {
 #endif
 
+/* Stays 1 while the library and its only binder (change3d_b200/_lib.py) ship together; descriptors only ever grow by
+ * appending fields (c3d_gemm_desc.flags was appended in round 1), entry points are only added. */
 #define C3D_ABI_VERSION 1
 
 /* status codes */
