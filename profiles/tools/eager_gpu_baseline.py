@@ -25,8 +25,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--tf32", action="store_true", help="allow TF32 in cuDNN / cuBLAS (default: fp32, like the reference)")
+    ap.add_argument("--device", default="cuda:0", help="cpu runs the same loop with a wall clock (logic check only)")
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = torch.device(a.device)
+    gpu = dev.type == "cuda"
     torch.backends.cudnn.benchmark = True                       # scripts/train_BCD.py:250-251
     torch.backends.cudnn.allow_tf32 = a.tf32
     torch.backends.cuda.matmul.allow_tf32 = a.tf32
@@ -38,21 +40,29 @@ def main() -> None:
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, 2e-4, (0.9, 0.99), eps=1e-8, weight_decay=1e-4)
     pre, post, target = (t.to(dev) for t in O.synth_inputs(a.batch, a.size, a.size, 16))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
+    if gpu:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = 0.0
     for it in range(a.warmup + a.steps):
         if it == a.warmup:
-            torch.cuda.synchronize()
-            e0.record()
+            if gpu:
+                torch.cuda.synchronize()
+                e0.record()
+            t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         loss = O.bce_dice_loss(O.trainer_forward(sd, "bcd", pre, post, True), target)
         loss.backward()
         opt.step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / a.steps
+    if gpu:
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+    else:
+        ms = (time.perf_counter() - t0) * 1e3 / a.steps
     print(json.dumps({"what": "oracle (torch eager ops) BCD train step on the GPU", "batch": a.batch, "size": a.size,
                       "tf32": a.tf32, "ms_per_step": round(ms, 2), "pairs_per_s": round(a.batch / ms * 1e3, 1),
-                      "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1), "loss": round(loss.item(), 5)}))
+                      "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1) if gpu else None, "loss": round(loss.item(), 5)}))
 
 
 if __name__ == "__main__":
