@@ -92,3 +92,18 @@ def test_product_path_fails_loudly_without_cuda():
     net = create_x3d(input_clip_length=3, depth_factor=5.0)
     with pytest.raises(RuntimeError, match="no CPU"):
         net.blocks[1](torch.zeros(1, 24, 3, 8, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: with the shared library absent, loading it — and therefore every op wrapper — raises."""
+    from change3d_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libchange3d_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU/eager fallback"):
+        _lib.load()
+    import torch
+    from change3d_b200 import losses
+    if not torch.cuda.is_available():
+        return
+    with pytest.raises(RuntimeError, match="no CPU/eager fallback"):      # on a GPU box: the op itself must raise too
+        losses.bce_dice_loss(torch.rand(4, device="cuda"), torch.zeros(4, device="cuda"))
