@@ -48,6 +48,8 @@ struct Params {
   int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
   int wait_hint;     // mbarrier try_wait suspend hint in ns (0 = none)
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
+  int pf_dist;       // TMA path: L2 prefetch distance in tiles (0 = off): the boxes of tile t + pf_dist are requested
+                     // when tile t's copies are issued, so HBM latency is paid ahead of the shared-memory pipeline
   uint32_t rps;      // rows per batch sample, clamped to 2^31 - 1 (M < 2^31: all row arithmetic fits 32 bits)
   unsigned long long* dbg;   // C3D_TC_DBG=1: per-warp wait/work cycle counters of one CTA ([32 warps][8]), else null
 };
@@ -305,6 +307,14 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
           mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
           tma_load_2d(dst, &tmA, c.chunk * KC, r0, bar);
           if (has2) tma_load_2d(dst + STAGE_FLOATS * 4, &tmA2, c.chunk * KC, r0, bar);
+          if (P.pf_dist) {
+            // the first tile also requests the tiles in between (nothing was requested for them yet)
+            for (int pt = c.ti == 0 ? 1 : c.ti + P.pf_dist; pt <= c.ti + P.pf_dist && pt < my_tiles; ++pt) {
+              const int pr = (int)((t_begin + pt) * BM);
+              tma_prefetch_2d(&tmA, c.chunk * KC, pr);
+              if (has2) tma_prefetch_2d(&tmA2, c.chunk * KC, pr);
+            }
+          }
         }
         __syncwarp();
       };
@@ -856,6 +866,15 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
     bool ok = tc::make_tmap_rows(&tmA, g.a.A, g.a.K, g.M, g.a.ld, tc::BM);
     if (ok && has2) ok = tc::make_tmap_rows(&tmA2, g.a.A2, g.a.K, g.M, g.a.ld, tc::BM);
     P.tma = ok ? 1 : 0;
+  }
+  P.pf_dist = 0;
+  if (P.tma) {
+    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : -1;      // -1 auto, 0 off, n tiles
+    const bool has2 = (g.a.mode == PRO_BNBWD || g.a.mode == PRO_ABSDIFF || g.a.mode == PRO_MASK_POS);
+    const long long tile_bytes = (long long)tc::BM * g.a.K * 4 * (has2 ? 2 : 1);
+    int d = (int)((128 * 1024 + tile_bytes - 1) / tile_bytes);
+    if (d > 8) d = 8;
+    P.pf_dist = pf_env < 0 ? d : (pf_env > 16 ? 16 : pf_env);
   }
   tc::Params Pb = P, Pc = P, Ph = P;
   int ns_b = 0, ns_c = 0, ns_h = 0;

@@ -38,6 +38,7 @@ struct Params {
   int nstage;
   int tmem_cols;
   int swap_lbo;            // bring-up switch: exchange the LBO / SBO fields of the MN-major descriptors
+  int pf_dist;             // L2 prefetch distance in stages (0 = off), counted from the stage being loaded
   uint32_t stage_bytes, off_blo, off_shi, off_slo, grp_bytes;
   unsigned long long* dbg;
 };
@@ -220,6 +221,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
           tma_load_2d(st + P.off_shi + (uint32_t)g * P.grp_bytes, &tmS, g * 32, r0, bar);
           if (small2) tma_load_2d(st + P.off_slo + (uint32_t)g * P.grp_bytes, &tmS2, g * 32, r0, bar);
         }
+        if (P.pf_dist) {      // L2 prefetch: stages beyond the ring (the first stage also requests the ones in between)
+          for (int pt = ti == 0 ? P.nstage : ti + P.pf_dist; pt <= ti + P.pf_dist && pt < my_tiles; ++pt) {
+            const int pr = (int)((t_begin + pt) * P.PT);
+            for (int g = 0; g < P.Gb; ++g) {
+              tma_prefetch_2d(&tmB, g * 32, pr);
+              if (big2) tma_prefetch_2d(&tmB2, g * 32, pr);
+            }
+            for (int g = 0; g < P.Gs; ++g) {
+              tma_prefetch_2d(&tmS, g * 32, pr);
+              if (small2) tma_prefetch_2d(&tmS2, g * 32, pr);
+            }
+          }
+        }
       }
       __syncwarp();
       if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
@@ -378,6 +392,14 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   if (nstage < 2) return -1;
   P.nstage = nstage;
   const size_t smem = (size_t)nstage * P.stage_bytes + tail;
+  {
+    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : -1;      // -1 auto, 0 off, n stages past the ring
+    auto two = [](const TileSrc& s) { return s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS; };
+    const long long raw = (long long)PT * 128 * (P.Gb * (two(P.big) ? 2 : 1) + P.Gs * (two(P.small) ? 2 : 1));
+    int d = (int)((128 * 1024 + raw - 1) / raw);
+    if (d > 12) d = 12;
+    P.pf_dist = pf_env == 0 ? 0 : nstage + (pf_env < 0 ? d : pf_env);
+  }
 
   CUtensorMap tmB, tmB2, tmS, tmS2;
   memset(&tmB, 0, sizeof(tmB)); memset(&tmB2, 0, sizeof(tmB2)); memset(&tmS, 0, sizeof(tmS)); memset(&tmS2, 0, sizeof(tmS2));

@@ -39,6 +39,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// L2 prefetch of one box of a tensor map (no shared memory, no barrier): issued a few tiles ahead of the loads so that
+// the bytes in flight from HBM are not bounded by the pipeline stages that fit in shared memory
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -116,16 +121,17 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, uint32_t sbo_
   return d;
 }
 
-// hi = x rounded to nearest TF32, lo = (x - hi) rounded to nearest TF32: both exactly representable, so the
-// tensor core's operand truncation is a no-op and the split error is unbiased (~2^-22 relative).
+// hi = x rounded to nearest TF32 (ties away from zero, what cvt.rna.tf32.f32 computes — done with two integer
+// instructions: the cvt compiles to four with its NaN / overflow guards, and the split runs once per staged
+// element, the producers' hottest arithmetic), lo = x - hi exactly (fp32, <= 13 significant bits).  The tensor core
+// reads the top 19 bits of an operand, so hi passes through unchanged and lo is truncated to its top 11 bits:
+// |error| <= 2^-22 |x|, of either sign (lo is symmetric around zero because hi is rounded to nearest).
 __device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = rna_tf32(x);
-  lo = rna_tf32(x - hi);
+  lo = x - hi;
 }
 __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
   split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);

@@ -100,9 +100,10 @@ class CaptionDecoder(nn.Module):
         self.wdc.bias.data.fill_(0)
         self.wdc.weight.data.uniform_(-0.1, 0.1)
 
-    def forward(self, memory, encoded_captions, caption_lengths):
-        """(memory (S,B,D), captions (B,L) int64, lengths (B,1)) -> (pred (B,L,V) sorted by length, sorted
-        captions, decode lengths, sort indices) — model/caption_decoder.py:574-612."""
+    def forward_device(self, memory, encoded_captions, caption_lengths):
+        """`forward` without the host read-back of the decode lengths (they stay a device tensor), so that a training
+        iteration can be captured in a CUDA graph: returns (pred sorted, sorted captions, decode lengths (B,) int64,
+        sort indices)."""
         tgt = encoded_captions.permute(1, 0)
         L = tgt.size(0)
         mask = torch.full((L, L), float('-inf'), device=tgt.device).triu(diagonal=1)
@@ -110,7 +111,20 @@ class CaptionDecoder(nn.Module):
         pred = self.transformer(emb, memory, tgt_mask=mask)
         pred = self.wdc(self.dropout_layer(pred)).permute(1, 0, 2)
         caption_lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
-        encoded_captions = encoded_captions[sort_ind]
-        pred = pred[sort_ind]
-        decode_lengths = (caption_lengths - 1).tolist()
-        return pred, encoded_captions, decode_lengths, sort_ind
+        return pred[sort_ind], encoded_captions[sort_ind], caption_lengths - 1, sort_ind
+
+    def forward(self, memory, encoded_captions, caption_lengths):
+        """(memory (S,B,D), captions (B,L) int64, lengths (B,1)) -> (pred (B,L,V) sorted by length, sorted
+        captions, decode lengths, sort indices) — model/caption_decoder.py:574-612."""
+        pred, encoded_captions, decode_lengths, sort_ind = self.forward_device(memory, encoded_captions, caption_lengths)
+        return pred, encoded_captions, decode_lengths.tolist(), sort_ind
+
+    def live_parameters(self):
+        """Parameters that `forward` uses, i.e. the ones that receive gradients (model/caption_decoder.py:411-423 runs
+        self_attn, norm1, multihead_attn2, norm2 of every layer; torch.optim.Adam skips the others because their
+        `.grad` stays None, so they are neither updated nor weight-decayed)."""
+        ps = [self.vocab_embedding.weight]
+        for layer in self.transformer.layers:
+            for m in (layer.self_attn, layer.multihead_attn2, layer.norm1, layer.norm2):
+                ps += list(m.parameters())
+        return ps + [self.wdc.weight, self.wdc.bias]

@@ -284,7 +284,8 @@ def dec_head_bwd(dpred, pred, X, w, is_sigmoid: bool, dW) -> torch.Tensor:
 
 
 def adam_step(p, g, m, v, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
-              grad_scale: float = 1.0) -> None:
+              grad_scale: float = 1.0, grad_clip: float = 0.0) -> None:
+    """grad_clip > 0: every scaled gradient element is clamped to +-grad_clip first (model/utils.py:481-491)."""
     _require_cuda(p, g, m, v)
     L.check(L.load().c3d_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
-                                   step, grad_scale, _stream()), "c3d_adam_step")
+                                   step, grad_scale, grad_clip, _stream()), "c3d_adam_step")

@@ -204,9 +204,10 @@ int c3d_convt_col2im(const float* U, const float* skip, long long skip_img_strid
 int c3d_convt_im2col(const float* d_out, float* V, int B, int h, int w, int cout, void* cuda_stream);
 
 /* torch.optim.Adam step (scripts/train_BCD.py:284-290: L2 weight decay added to the gradient) on flat, 16-byte
- * aligned fp32 buffers; g is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+ * aligned fp32 buffers; g is multiplied by grad_scale first (1/world_size after a sum all-reduce), then clamped to
+ * [-grad_clip, grad_clip] when grad_clip > 0 (clip_gradient, model/utils.py:481-491; scripts/train_CC.py:141-144). */
 int c3d_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, float grad_scale, void* cuda_stream);
+                  float eps, float weight_decay, int step, float grad_scale, float grad_clip, void* cuda_stream);
 
 /* ============================== losses and metrics ==============================
  * Every forward is one streaming pass: partial sums go to a small device workspace `ws` (C3D_LOSS_WS_BYTES,

@@ -10,8 +10,22 @@ import argparse
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("CHANGE3D_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pv_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "pv_shim")
+
+
+def _resolve_root() -> str:
+    """CHANGE3D_REFERENCE_ROOT, else /root/reference (authoring container), else the byte-identical copy that
+    `oracle/build_ref.py` staged under oracle/_ref/ (the only one that exists on the GPU box)."""
+    env = os.environ.get("CHANGE3D_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/model/trainer.py"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:

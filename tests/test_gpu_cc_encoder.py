@@ -40,20 +40,40 @@ def test_cc_feature_path_forward_backward(golden_dir):
     log(f"cc feature path out: |mine-fp64| {e_mine:.3e}  |reference_fp32-fp64| {e_ref:.3e}")
     assert e_mine <= max(8 * e_ref, 1e-3)                     # north_star: forward within 1e-3 relative
     named = dict(enc.named_parameters())
-    # 55 residual blocks whose last 15 normalise over 24 samples per channel: the chain amplifies fp32 rounding
-    # chaotically (ReLU-mask flips).  torch's own fp32 run differs from fp64 by up to 1e-2 on these tensors here and
-    # by 3e-2 .. 0.3 at 64x64, so the yardstick is the chain's fp32 noise (largest reference-fp32-vs-fp64 error over
-    # the tensors), not the per-tensor one: a wrong kernel shows up as O(1).  The res5-shaped kernels themselves
-    # are held to 4x the per-tensor fp32 noise at depth 3 in test_res_stage_backward (2.5e-6 measured).
-    errs = {k: (rel_err(named[k].grad, s64["encoder." + k].grad), rel_err(g["grad:" + k], s64["encoder." + k].grad))
-            for k in GRAD_KEYS}
-    chain_noise = max(e_ref for _, e_ref in errs.values())
+    # Yardstick.  This case runs res5 at 2x2 pixels: every BatchNorm there normalises over B*T*H*W = 24 samples, and one
+    # ReLU decision of a near-zero activation that comes out differently moves a weight-gradient row by O(1/24) and
+    # everything upstream of it by as much.  profiles/r02_error_growth.md shows it block by block (torch fp32, the
+    # tcgen05 path and the FFMA path are all at 3e-5 behind a flip and at 2e-2 .. 2.5e-1 in front of one) and in PURE
+    # fp64: perturbing the input images by a relative 1e-6 moves these gradients by 2e-2 .. 2.4e-1, the last block's
+    # conv_c row by exactly the 0.20 an fp32 run shows when it draws that flip.  So an fp32 implementation's gradient
+    # here is one sample of "the fp64 gradient under fp32-sized forward noise", and the test draws that distribution
+    # itself: 8 fp64 runs with the inputs perturbed by 1e-6 (forward output moves 6e-4 .. 1e-3; torch fp32 itself sits
+    # at 2.3e-4).  Per tensor: the 95th-percentile element error (insensitive to one flipped row) must be within 4x
+    # the larger of torch-fp32's and the samples' 95th percentile, and the max error within 2x the largest sample's.
+    def elem_err(got, ref64):
+        return ((torch.as_tensor(np.asarray(got)).double() - ref64).abs() / (ref64.abs().max() + 1e-300)).reshape(-1)
+
+    samples = {k: [] for k in GRAD_KEYS}
+    for sd_ in range(8):
+        gen = torch.Generator().manual_seed(1000 + sd_)
+        p2 = pre.double() * (1 + 1e-6 * torch.randn(pre.shape, generator=gen, dtype=torch.float64))
+        q2 = post.double() * (1 + 1e-6 * torch.randn(post.shape, generator=gen, dtype=torch.float64))
+        sp = O.clone_sd(full, dtype=torch.float64, requires_grad=True)
+        (O.encoder_forward(sp, p2, q2, 1, True, output_final=True) * weights(SEED).double()).sum().backward()
+        for k in GRAD_KEYS:
+            samples[k].append(elem_err(sp["encoder." + k].grad, s64["encoder." + k].grad))
     bad = []
-    for k, (e_mine, e_ref) in errs.items():
-        log(f"cc grad {k}: |mine-fp64| {e_mine:.3e}  |reference_fp32-fp64| {e_ref:.3e}")
-        if e_mine > max(8.0 * e_ref, 15.0 * chain_noise):       # measured 6.1e-2 .. 6.8e-2 vs chain noise 1.0e-2
-            bad.append((k, e_mine, e_ref))
-    assert not bad, (bad, chain_noise)
+    for k in GRAD_KEYS:
+        t64 = s64["encoder." + k].grad
+        e_mine, e_ref = elem_err(named[k].grad.cpu(), t64), elem_err(g["grad:" + k], t64)
+        q = lambda e: torch.quantile(e, 0.95).item()                     # noqa: E731
+        q_yard = max([q(e_ref)] + [q(e) for e in samples[k]])
+        m_yard = max([e_ref.max().item()] + [e.max().item() for e in samples[k]])
+        log(f"cc grad {k}: max |mine-fp64| {e_mine.max().item():.3e} (reference_fp32 {e_ref.max().item():.3e}, fp64 samples "
+            f"up to {m_yard:.3e});  q95 mine {q(e_mine):.3e} (reference_fp32 {q(e_ref):.3e}, samples up to {q_yard:.3e})")
+        if q(e_mine) > max(4.0 * q_yard, 1e-5) or e_mine.max().item() > max(2.0 * m_yard, 1e-4):
+            bad.append((k, e_mine.max().item(), q(e_mine), m_yard, q_yard))
+    assert not bad, bad
     k = "x3d.blocks.4.res_blocks.14.branch2.norm_c.running_mean"
     assert rel_err(enc.state_dict()[k], g["stat:" + k]) < 1e-3
     # parameters the path never reaches (enhance convs, classification head blocks.5) receive no gradient

@@ -198,6 +198,9 @@ def test_train_step_confusion_matrix_eager_and_graph():
             torch.manual_seed(16)                              # so rebuild the model for the timed comparison
             model = build_trainer("bcd", H, W, 1).train()
             want_first = O.confusion_matrix(2, target.cpu().numpy(), (first_pred > 0.5).long().cpu().numpy())
+            # pixels whose probability sits within 1e-3 of the threshold: the only ones that two
+            # runs differing in the last bits (atomics order) may classify differently; each moves two matrix cells
+            inside = int(((first_pred - 0.5).abs() <= 1e-3).sum().item())
         step = BCDTrainStep(model, lr=2e-4, use_graph=use_graph)
         losses_, cms = [], []
         for _ in range(3):
@@ -205,14 +208,14 @@ def test_train_step_confusion_matrix_eager_and_graph():
             cms.append(step.cm.cpu().numpy().copy())
         assert cms[-1].sum() == 3 * B * H * W
         if not use_graph:
-            assert np.abs(cms[0] - want_first).sum() <= 4        # a pixel within fp32 noise of 0.5 may flip
+            assert np.abs(cms[0] - want_first).sum() <= 2 * inside, (cms[0], want_first, inside)
         sc = step.scores()
         ref = O.cm_scores(cms[-1])
         assert all(abs(sc[k] - ref[k]) < 1e-12 or (np.isnan(sc[k]) and np.isnan(ref[k])) for k in ref)
         results.append((losses_, cms))
     (l_e, cm_e), (l_g, cm_g) = results
     log("train-step losses eager " + " ".join(f"{v:.5f}" for v in l_e) + " | graph " + " ".join(f"{v:.5f}" for v in l_g))
-    assert np.abs(cm_e[0] - cm_g[0]).sum() <= 4                # first step: identical weights, same mask up to ties
+    assert np.abs(cm_e[0] - cm_g[0]).sum() <= 2 * inside, (cm_e[0], cm_g[0], inside)   # same weights: margin pixels only
     assert abs(l_e[0] - l_g[0]) < 1e-5 and all(abs(a - b) < 5e-3 for a, b in zip(l_e, l_g))
     assert l_e[-1] < l_e[0]
 

@@ -76,7 +76,9 @@ def test_task_loss_and_gradients_vs_oracle(task, ncls):
             out = O.trainer_forward(O.clone_sd(sd), task, pre, post, True)[2]
         want_cm = O.confusion_matrix(2, labels[2].unsqueeze(1).float().numpy(), (out > 0.5).long().numpy())
         got_cm = step.cm.cpu().numpy()
-        assert got_cm.sum() == B * H * W and np.abs(got_cm - want_cm).sum() <= 4      # threshold ties at fp32 noise
+        # only pixels within 1e-3 of the threshold may be classified differently (each moves two matrix cells)
+        inside = int(((out - 0.5).abs() <= 1e-3).sum())
+        assert got_cm.sum() == B * H * W and np.abs(got_cm - want_cm).sum() <= 2 * inside, (got_cm, want_cm, inside)
 
 
 @pytest.mark.parametrize("task,ncls", [("scd", 7), ("bda", 5)])
