@@ -1,18 +1,31 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: bi-temporal pairs/sec, X3D-L BCD train step (fwd + BCEDiceLoss + bwd + Adam),
-synthetic LEVIR-shape 256x256, batch 32 per GPU (BASELINE.json configs[1]).
+"""Benchmark of the hot path: bi-temporal pairs/sec of one X3D-L training step at 256x256, synthetic data.
 
-    python bench.py --gpus N --steps K --warmup W          # our arm (N > 1: launched by torchrun, one rank per GPU)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle) on host cores
+    python bench.py --gpus N --steps K --warmup W            # BASELINE.json configs[1]: BCD train, batch 32 per GPU
+    python bench.py --task scd|bda|cc ...                    # configs[2..4]: SCD (B=16, T=5, three heads), BDA (B=32, T=4,
+                                                             #   two heads), CC (B=16, encoder to res5 + caption decoder)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU implementation of the step
 
-Prints ONE JSON line on rank 0.  `value` = whole-job pairs/s with the inputs resident in HBM; `e2e` = the same
-step through the public API (change3d_b200.input_pipeline.DevicePrefetcher feeding change3d_b200.train_step.BCDTrainStep)
-with pinned HOST inputs: every step's H2D copy (on a copy stream, one batch ahead) and a D2H read of its loss are inside
-the timed region (--e2e-mode plain: copies on the compute stream; both: measure both).  `roofline` describes the kernel family that takes the most device
-time, from CUDA events recorded around every launch of a separate profiled step; `cpu_baseline` times the
-oracle (a port of the reference algorithm, oracle/change3d_oracle.py) on this box's host cores.
+(N > 1: launched by torchrun, one rank per GPU.)  Prints ONE JSON line on rank 0.
+
+  value      whole-job pairs/s, inputs resident in HBM, K steps timed with CUDA events, max over ranks.
+  e2e        the same step through the public API (change3d_b200.input_pipeline.DevicePrefetcher feeding
+             change3d_b200.train_step.*TrainStep) with pinned HOST inputs: every step's H2D copy and a D2H read of its
+             loss are inside the timed region.
+  roofline   the kernel family with the most device time (CUDA events around every launch of a separate profiled step).
+             `frac` = SURVEY.md section 8(d) bytes (each conv reads its input once, writes its output once, + weights;
+             BN / activations / residuals free) of that family's launches / their time / measured HBM peak;
+             `frac_design` counts every operand tensor of the fused design, `frac_dram` the DRAM bytes of the committed
+             ncu pass; `step_frac` = 3 x forward bytes per pair x batch (section 8(d)'s training model) / step time / peak.
+  cpu_baseline  the reference's own modules (oracle/_ref, staged by build(); else the oracle port) on this box's host
+             cores: a bounded train-step sample and the B=1 eval forward of BASELINE.json configs[0];
+             `parity_256` = this engine against that CPU leg's outputs on the same 256x256 inputs and weights.
+  gpu_eager_baseline  the reference algorithm as eager torch ops on a B200 (measured with
+             profiles/tools/eager_gpu_baseline.py, value read from profiles/r02_eager_gpu_baseline.json).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -23,8 +36,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "bi-temporal pairs/sec (X3D-L BCD train step, 256x256)"
 UNIT = "pairs/s"
+# per task: per-GPU batch (the reference's --batch_size is per process), perception frames, classes, Trainer dataset key,
+# forward bytes per pair of SURVEY.md section 8(d) (fp32 storage), BASELINE.json config index
+TASKS = {
+    "bcd": dict(batch=32, P=1, ncls=1, dataset="LEVIR-CD", fwd_bytes=1161e6, cfg=1,
+                what="BCD X3D-L train (fwd+BCEDiceLoss+bwd+Adam), synthetic LEVIR-shape"),
+    "scd": dict(batch=16, P=3, ncls=7, dataset="SECOND", fwd_bytes=1953e6, cfg=2,
+                what="SCD X3D-L train (T=5, three decoder heads, 0.5*(CE+CE)+BCEDice+ChangeSimilarity, bwd, Adam), "
+                     "synthetic SECOND-shape"),
+    "bda": dict(batch=32, P=2, ncls=5, dataset="xBD", fwd_bytes=1556e6, cfg=3,
+                what="BDA X3D-L train (T=4, two decoder heads, CE+BCEDice, bwd, Adam), synthetic xBD-shape"),
+    "cc": dict(batch=16, P=1, ncls=1, dataset="LEVIR-CC", fwd_bytes=1247e6, cfg=4, vocab=501, cap_len=52,
+               what="CC X3D-L train (encoder to res5 + caption_decoder transformer head, packed CE, clamp +-5, two Adams), "
+                    "synthetic LEVIR-CC-shape"),
+}
+
+
+def metric_name(task):
+    return f"bi-temporal pairs/sec (X3D-L {task.upper()} train step, 256x256)"
 
 
 def parse():
@@ -33,7 +63,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (reference --batch_size is per process)")
+    ap.add_argument("--task", default="bcd", choices=list(TASKS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the task's BASELINE.json batch)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of a captured CUDA graph")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU-baseline sample")
@@ -54,50 +85,158 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def model_args(task, size):
+    t = TASKS[task]
+    ns = argparse.Namespace(num_perception_frame=t["P"], num_class=t["ncls"], in_height=size, in_width=size,
+                            dataset=t["dataset"], pretrained="/nonexistent/X3D_L.pyth")
+    if task == "cc":                       # scripts/train_CC.py:553-580 defaults
+        ns.vocab_size, ns.embed_dim, ns.n_head, ns.n_layer, ns.dropout = t["vocab"], 192, 8, 3, 0.1
+    return ns
+
+
+def synth_batch(task, B, S, gen):
+    """Host tensors of one batch: (pre, post, *labels) with the label statistics of SURVEY.md section 8(d)."""
+    import torch
+    t = TASKS[task]
+    pre = torch.randn(B, 3, S, S, generator=gen)
+    post = torch.randn(B, 3, S, S, generator=gen)
+    if task == "bcd":
+        return pre, post, (torch.rand(B, 1, S, S, generator=gen) < 0.05).float()
+    if task == "scd":                      # scripts/train_SCD.py:205-217
+        change = (torch.rand(B, S, S, generator=gen) < 0.2).long()
+        return (pre, post, torch.randint(1, t["ncls"], (B, S, S), generator=gen),
+                torch.randint(1, t["ncls"], (B, S, S), generator=gen), change)
+    if task == "bda":                      # scripts/train_BDA.py:174-181
+        loc = (torch.rand(B, S, S, generator=gen) < 0.1).float()
+        return pre, post, loc, (loc * torch.randint(1, t["ncls"], (B, S, S), generator=gen)).long()
+    caps = torch.randint(1, t["vocab"], (B, t["cap_len"]), generator=gen)
+    lens = torch.randint(5, 41, (B, 1), generator=gen)
+    for b in range(B):
+        caps[b, int(lens[b]):] = 0
+    return pre, post, caps, lens
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on host cores
+# CPU arm: the reference's own modules (oracle/_ref through oracle/pv_shim), else the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_train_steps(batch: int, size: int, steps: int, warmup: int):
-    """BCD train step exactly as scripts/train_BCD.py:179-216 (update_bcd, BCEDiceLoss, backward, Adam) with the
-    oracle's functional model.  Returns (pairs/s, threads, seconds per step)."""
+def _reference_kind():
+    from oracle import build_ref, reference_loader
+    if reference_loader.available() or build_ref.staged():
+        return "reference"
+    return "port"
+
+
+def cpu_reference_leg(task, batch, size, steps, warmup, want_outputs=False):
+    """The BCD/SCD/BDA train step exactly as scripts/train_*.py run it (update_<task>, the script's loss, backward,
+    torch.optim.Adam(2e-4, betas (0.9, 0.99), wd 1e-4)) on host cores: with the reference's own `model/trainer.py`
+    Trainer and `model/utils.py` losses when they are staged (kind "reference"), else with the oracle port.  Weights =
+    oracle.synth_state_dict(seed 16), inputs = oracle.synth_inputs(seed 16) — what `parity_256` replays on the GPU.
+    Returns dict(pairs_per_s, threads, sec, kind, eval_fwd_b1, outputs (first-step train-mode predictions), loss)."""
     import torch
     from oracle import change3d_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = O.synth_state_dict(O.trainer_schema("bcd", 1, size, size, 1), 16)
-    sd = O.clone_sd(sd, requires_grad=True)
-    params = [v for k, v in sd.items() if v.requires_grad]
-    opt = torch.optim.Adam(params, 2e-4, (0.9, 0.99), eps=1e-8, weight_decay=1e-4)
+    t = TASKS[task]
+    kind = _reference_kind() if task != "cc" else "port"
+    sd = O.synth_state_dict(O.trainer_schema(task if task != "cc" else "bcd", t["P"], size, size, t["ncls"]), 16)
     pre, post, target = O.synth_inputs(batch, size, size, 16)
+    labels = (target,) if task == "bcd" else O.synth_labels(task, batch, size, size, t["ncls"], 16)
+    res = {"kind": kind, "threads": torch.get_num_threads()}
+    if kind == "reference":
+        from oracle import reference_loader as R
+        ref = R.load()
+        import model.utils as MU                        # the reference's file (losses), unchanged
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref.Trainer(R.make_args(task, size, size, t["ncls"])).float()
+        model.load_state_dict(sd, strict=True)
+        params = list(model.parameters())
+        ce0, sim = MU.CrossEntropyLoss2d(ignore_index=0), MU.ChangeSimilarity()
+
+        def fwd_loss():
+            if task == "bcd":
+                out = model.update_bcd(pre, post)
+                return (out,), MU.BCEDiceLoss(out, labels[0])
+            if task == "scd":                           # scripts/train_SCD.py:212-229
+                pl, ql, ch = labels
+                pl, ql = pl * ch, ql * ch
+                a, b, c = model.update_scd(pre, post)
+                loss = 0.5 * (ce0(a, pl) + ce0(b, ql)) + MU.BCEDiceLoss(c, ch.unsqueeze(1).float()) + sim(a[:, 1:], b[:, 1:], ch.unsqueeze(1))
+                return (a, b, c), loss
+            loc, cls = labels                           # scripts/train_BDA.py:180-199
+            a, b = model.update_bda(pre, post)
+            return (a, b), ce0(a, cls) + MU.BCEDiceLoss(b, loc.unsqueeze(1))
+
+        def eval_fwd(x, y):
+            model.eval()
+            with torch.no_grad():
+                getattr(model, "update_" + task)(x, y)
+            model.train()
+    else:
+        osd = O.clone_sd(sd, requires_grad=True)
+        params = [v for v in osd.values() if v.requires_grad]
+
+        def fwd_loss():
+            if task == "cc":
+                feat = O.encoder_forward(osd, pre, post, 1, True, output_final=True)
+                return (feat,), (feat * feat).mean()    # encoder-only stand-in (the port has no caption head)
+            outs = O.trainer_forward(osd, task, pre, post, True)
+            return ((outs,) if task == "bcd" else tuple(outs)), O.task_loss(task, outs, labels)
+
+        def eval_fwd(x, y):
+            with torch.no_grad():
+                if task == "cc":
+                    O.encoder_forward(osd, x, y, 1, False, output_final=True)
+                else:
+                    O.trainer_forward(osd, task, x, y, False)
+    model_train = True
+    opt = torch.optim.Adam(params, 2e-4, (0.9, 0.99), eps=1e-8, weight_decay=1e-4)      # scripts/train_BCD.py:284-290
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        loss = O.bce_dice_loss(O.trainer_forward(sd, "bcd", pre, post, True), target)
+        outs, loss = fwd_loss()
+        if it == 0 and want_outputs:
+            res["outputs"] = [o.detach().clone() for o in outs]
+            res["loss"] = float(loss.detach())
         loss.backward()
         opt.step()
-        float(loss)
+        float(loss.detach())
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    sec = sum(times) / len(times)
-    return batch / sec, torch.get_num_threads(), sec
+    sec = sum(times) / max(1, len(times))
+    res.update(pairs_per_s=batch / sec, sec=sec, sd=sd, inputs=(pre, post) + tuple(labels))
+    # BASELINE.json configs[0]: eval forward of ONE pair (B=1) on the CPU, the reference's plumbing case
+    x1, y1 = pre[:1], post[:1]
+    eval_fwd(x1, y1)
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        eval_fwd(x1, y1)
+    res["eval_fwd_b1"] = n / (time.perf_counter() - t0)
+    del model_train
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    task = args.task
     steps = max(1, min(args.steps, 3))          # bounded: each step is ~seconds of CPU work
     warm = 1
     t_start = time.perf_counter()
-    v, threads, sec = cpu_train_steps(args.cpu_batch, args.size, steps, warm)
-    sample = (f"BCD train step (fwd+BCEDice+bwd+Adam) batch {args.cpu_batch} at {args.size}x{args.size}, "
-              f"{steps} timed steps after {warm} warm-up, oracle port of the reference on torch CPU ops")
-    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+    r = cpu_reference_leg(task, args.cpu_batch, args.size, steps, warm)
+    v = r["pairs_per_s"]
+    impl = ("the reference's own model/trainer.py + model/utils.py (oracle/_ref, through oracle/pv_shim) on torch CPU ops"
+            if r["kind"] == "reference" else "oracle port of the reference on torch CPU ops")
+    sample = (f"{task.upper()} train step (fwd+loss+bwd+Adam) batch {args.cpu_batch} at {args.size}x{args.size}, "
+              f"{steps} timed steps after {warm} warm-up, {impl}")
+    line = {"impl": "reference", "metric": metric_name(task), "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": round(r["sec"] * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BCD X3D-L train, synthetic {args.size}x{args.size}, CPU sample batch {args.cpu_batch}",
-                       "note": "reference CPU path = oracle port (reference needs pytorchvideo/fvcore, absent offline)"},
-            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": f"{TASKS[task]['what']} {args.size}x{args.size}, CPU sample batch {args.cpu_batch}",
+                       "note": "reference CPU path; pytorchvideo/fvcore classes from oracle/pv_shim (absent offline)"},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample,
+                             "eval_fwd_b1_pairs_per_s": round(r["eval_fwd_b1"], 3)},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t_start, 1)}
     print(json.dumps(line), flush=True)
@@ -141,6 +280,54 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def build_step(task, size, dev, use_graph):
+    import torch
+    from change3d_b200.model.trainer import Trainer
+    from change3d_b200.train_step import CCTrainStep, TrainStep
+    torch.manual_seed(16)                                   # scripts/train_BCD.py:253 (identical init on every rank)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Trainer(model_args(task, size)).to(dev).float()
+    if task == "cc":
+        return model, CCTrainStep(model, use_graph=use_graph)
+    return model, TrainStep(model, lr=2e-4, use_graph=use_graph, task=task)
+
+
+def parity_256(task, leg, dev):
+    """This engine against the CPU leg on the same weights and 256x256 inputs: train-mode head outputs of the first
+    step (max abs error / max abs reference; decisions that differ outside the 1e-3 margin) and the loss."""
+    import torch
+    from change3d_b200.model.trainer import Trainer
+    from change3d_b200.train_step import TrainStep
+    size = leg["inputs"][0].shape[-1]
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Trainer(model_args(task, size))
+    model.load_state_dict(leg["sd"], strict=True)
+    model = model.to(dev).float().train()
+    step = TrainStep(model, task=task)
+    loss = float(step._iteration(*[t.to(dev) for t in leg["inputs"]]).item())
+    with torch.no_grad():
+        outs = getattr(model, "update_" + task)(leg["inputs"][0].to(dev), leg["inputs"][1].to(dev))
+    outs = [outs] if task == "bcd" else list(outs)
+    max_rel, flips, inside = 0.0, 0, 0
+    for got, ref in zip(outs, leg["outputs"]):
+        got = got.float().cpu()
+        max_rel = max(max_rel, ((got - ref).abs().max() / ref.abs().max()).item())
+        if ref.shape[1] == 1:
+            safe = (ref - 0.5).abs() > 1e-3
+            diff = (got > 0.5) != (ref > 0.5)
+        else:
+            top2 = ref.topk(2, dim=1).values
+            safe = (top2[:, 0] - top2[:, 1]) > 1e-3 * ref.abs().max()
+            diff = got.argmax(1) != ref.argmax(1)
+        flips += int((diff & safe).sum())
+        inside += int((~safe).sum())
+    del model, step
+    torch.cuda.empty_cache()
+    return {"against": leg["kind"], "batch": leg["inputs"][0].shape[0], "size": size, "max_rel": round(max_rel, 7),
+            "mask_flips": flips, "pixels_inside_margin": inside, "loss": round(loss, 6), "loss_cpu": round(leg["loss"], 6),
+            "loss_rel": round(abs(loss - leg["loss"]) / max(1.0, abs(leg["loss"])), 8), "tolerance": 1e-3}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -155,27 +342,18 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    import argparse as _ap
-    import contextlib
-    import io
     from change3d_b200 import _lib, ops
-    from change3d_b200.model.trainer import Trainer
-    from change3d_b200.train_step import BCDTrainStep
     _lib.load()
 
-    B, S = args.batch, args.size
-    margs = _ap.Namespace(num_perception_frame=1, num_class=1, in_height=S, in_width=S, dataset="LEVIR-CD",
-                          pretrained="/nonexistent/X3D_L.pyth")
-    torch.manual_seed(16)                                   # scripts/train_BCD.py:253 (identical init on every rank)
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = Trainer(margs).to(dev).float()
-    step = BCDTrainStep(model, lr=2e-4, use_graph=not args.no_graph)
+    task = args.task
+    T = TASKS[task]
+    B, S = (args.batch or T["batch"]), args.size
+    model, step = build_step(task, S, dev, not args.no_graph)
 
     g = torch.Generator(device="cpu").manual_seed(16 + rank)
-    h_pre = torch.randn(B, 3, S, S, generator=g).pin_memory()
-    h_post = torch.randn(B, 3, S, S, generator=g).pin_memory()
-    h_tgt = (torch.rand(B, 1, S, S, generator=g) < 0.05).float().pin_memory()
-    pre, post, tgt = h_pre.to(dev), h_post.to(dev), h_tgt.to(dev)
+    host = tuple(t.pin_memory() for t in synth_batch(task, B, S, g))
+    devt = tuple(t.to(dev) for t in host)
+    h2d = sum(t.numel() * t.element_size() for t in host)
 
     def barrier():
         if world > 1:
@@ -185,11 +363,9 @@ def run_ours(args):
     # ---- warm-up (>= 3) ----
     W = max(3, args.warmup)
     for _ in range(W):
-        loss = step(pre, post, tgt)
+        loss = step(*devt)
     barrier()
     launches_before = _lib.LAUNCHES[0]
-    if step.graph is None:
-        pass
 
     # ---- timed region: K steps, device resident inputs ----
     sampler = ClockSampler(local)
@@ -198,7 +374,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = step(pre, post, tgt)
+        loss = step(*devt)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -226,20 +402,22 @@ def run_ours(args):
 
     def host_batches(n):
         for _ in range(n):
-            yield (h_pre, h_post, h_tgt)
+            yield host
+
+    scratch = tuple(torch.empty_like(t) for t in devt)
 
     def e2e_plain(n):
         for _ in range(n):
-            d_pre.copy_(h_pre, non_blocking=True); d_post.copy_(h_post, non_blocking=True); d_tgt.copy_(h_tgt, non_blocking=True)
-            float(step(d_pre, d_post, d_tgt).item())
+            for d, h in zip(scratch, host):
+                d.copy_(h, non_blocking=True)
+            float(step(*scratch).item())
 
     def e2e_prefetch(n):
         pf = DevicePrefetcher(host_batches(n), dev)
-        for a_, b_, c_ in pf:
-            float(step(a_, b_, c_).item())
-        assert pf.bytes_staged == n * (h_pre.numel() + h_post.numel() + h_tgt.numel()) * 4
+        for batch in pf:
+            float(step(*batch).item())
+        assert pf.bytes_staged == n * h2d
 
-    d_pre, d_post, d_tgt = torch.empty_like(pre), torch.empty_like(post), torch.empty_like(tgt)
     e2e_runs = {}
     for mode in (("plain", "prefetch") if args.e2e_mode == "both" else (args.e2e_mode,)):
         fn = e2e_plain if mode == "plain" else e2e_prefetch
@@ -254,21 +432,22 @@ def run_ours(args):
         e2e_runs[mode] = world * B * k2 / float(te.item())
     e2e_mode = args.e2e_mode if args.e2e_mode != "both" else max(e2e_runs, key=e2e_runs.get)
     e2e_value = e2e_runs[e2e_mode]
-    h2d = (h_pre.numel() + h_post.numel() + h_tgt.numel()) * 4
-    # training confusion matrix hist[target][output > 0.5], accumulated on the device by the loss kernel over every
-    # step since the graph was captured (the reference copies a 16.8 MB mask to the host per step for this); one
-    # 32-byte read-back here, outside both timed regions
-    cm_host = step.cm.cpu().tolist()
+    # training confusion matrix hist[target][output > 0.5] of the binary head, accumulated on the device by the loss
+    # kernel over every step since the graph was captured; one 32-byte read-back here, outside both timed regions
+    cm_host = step.cm.cpu().tolist() if getattr(step, "cm", None) is not None else None
 
     # ---- roofline probe: one eager step with CUDA events around every launch ----
     roofline = None
     families = {}
+    peak, peak_src = peaks()
     if not args.skip_roofline and rank == 0:
         # rank-local: the probe must not enter a collective (only rank 0 runs it), so it sequences the iteration
-        # and the Adam step itself instead of calling the DDP-aware BCDTrainStep.__call__
+        # and the Adam step(s) itself instead of calling the DDP-aware __call__
         def probe():
-            step._iteration(pre, post, tgt)
+            step._iteration(*devt)
             step.opt.step()
+            if task == "cc":
+                step.dec_opt.step()
         # per-launch durations are only meaningful for kernels that run alone: the probe keeps the weight-gradient
         # GEMMs on the main stream (the timed steps above overlap them with the dgrad chain on a side stream)
         side_prev = os.environ.get("C3D_SIDE_STREAM")
@@ -286,62 +465,94 @@ def run_ours(args):
         prof, ops.PROF = ops.PROF, None
         tot_ms = 0.0
         for fam, recs in prof.items():
-            t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-            nb = sum(n for _, _, n in recs)
+            t_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
+            nb = sum(r[2] for r in recs)
+            nb_model = sum(r[3] for r in recs)
             families[fam] = {"ms_per_step": round(t_ms / 2, 3), "launches_per_step": len(recs) // 2,
-                             "algorithmic_GB_per_step": round(nb / 2 / 1e9, 3),
-                             "achieved_GBs": round(nb / (t_ms / 1e3) / 1e9, 1) if t_ms > 0 else None}
+                             "algorithmic_GB_per_step": round(nb_model / 2 / 1e9, 3),
+                             "design_GB_per_step": round(nb / 2 / 1e9, 3),
+                             "achieved_GBs": round(nb_model / (t_ms / 1e3) / 1e9, 1) if t_ms > 0 else None}
             tot_ms += t_ms / 2
         top = max(families, key=lambda k: families[k]["ms_per_step"])
-        peak, peak_src = peaks()
-        ach = families[top]["achieved_GBs"]
+        f = families[top]
+        ach = f["achieved_GBs"]
+        ach_design = f["design_GB_per_step"] * 1e3 / f["ms_per_step"]
         # measured DRAM traffic per launch of this kernel family, from the committed ncu pass (never measured here:
         # a number taken under a profiler is not a bench value, the traffic of a launch does not depend on timing)
         traffic, traffic_src = None, None
-        for tname in ("r01b_traffic.json", "r01_traffic.json"):          # latest committed launch list first
+        for tname in ("r02_traffic.json", "r01b_traffic.json"):          # latest committed launch list first
             tpath = os.path.join(ROOT, "profiles", tname)
-            if not os.path.isfile(tpath):
+            if task != "bcd" or not os.path.isfile(tpath):
                 continue
-            with open(tpath) as f:
-                tj = json.load(f)
+            with open(tpath) as fh:
+                tj = json.load(fh)
             if top in tj.get("families", {}):
                 traffic = tj["families"][top]["dram_bytes_per_launch"]
                 traffic_src = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
                 break
-        alg_per_launch = int(families[top]["algorithmic_GB_per_step"] * 1e9 / max(1, families[top]["launches_per_step"]))
+        nl = max(1, f["launches_per_step"])
+        step_bytes = 3.0 * T["fwd_bytes"] * B
         roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
-                    "share_of_step": round(families[top]["ms_per_step"] / max(tot_ms, 1e-9), 3),
+                    "frac": round(ach / peak, 4),
+                    "frac_design": round(ach_design / peak, 4),
+                    "frac_dram": round(traffic * nl / (f["ms_per_step"] / 1e3) / 1e9 / peak, 4) if traffic else None,
+                    "step_frac": round(step_bytes / (ms_per_step / 1e3) / 1e9 / peak, 4),
+                    "step_algorithmic_GB": round(step_bytes / 1e9, 2),
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": int(f["algorithmic_GB_per_step"] * 1e9 / nl),
+                    "bytes_model": "SURVEY.md 8(d): per conv launch 4*(M*K_in + M*N_out + K_in*N_out), logical channels; "
+                                   "step = 3 x forward bytes/pair x batch",
+                    "peak_source": peak_src,
+                    "share_of_step": round(f["ms_per_step"] / max(tot_ms, 1e-9), 3),
                     "families": families}
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on host cores ----
-    cpu = None
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on host cores + 256x256 parity ----
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        v, threads, sec = cpu_train_steps(args.cpu_batch, S, args.cpu_steps, 1)
-        cpu = {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"BCD train step batch {args.cpu_batch} at {S}x{S}, {args.cpu_steps} timed steps after 1 warm-up "
-                         f"({sec:.2f} s/step), oracle port on torch CPU ops"}
+        leg = cpu_reference_leg(task, args.cpu_batch, S, args.cpu_steps, 1, want_outputs=(task != "cc"))
+        src = ("the reference's model/trainer.py + model/utils.py (oracle/_ref via oracle/pv_shim)" if leg["kind"] == "reference"
+               else "oracle port")
+        cpu = {"value": round(leg["pairs_per_s"], 4), "unit": UNIT, "cores": leg["threads"], "kind": leg["kind"],
+               "sample": f"{task.upper()} train step batch {args.cpu_batch} at {S}x{S}, {args.cpu_steps} timed steps after 1 "
+                         f"warm-up ({leg['sec']:.2f} s/step), {src} on torch CPU ops",
+               "eval_fwd_b1_pairs_per_s": round(leg["eval_fwd_b1"], 3),
+               "eval_fwd_b1_note": "BASELINE.json configs[0]: eval forward of one 256x256 pair, batch 1, CPU"}
+        if task != "cc":
+            parity = parity_256(task, leg, dev)
+
+    eager = None
+    epath = os.path.join(ROOT, "profiles", "r02_eager_gpu_baseline.json")
+    if task == "bcd" and os.path.isfile(epath):
+        with open(epath) as fh:
+            ej = json.load(fh)
+        eager = {"value": ej["pairs_per_s"], "unit": UNIT, "ms_per_step": ej["ms_per_step"], "batch": ej["batch"],
+                 "source": "profiles/r02_eager_gpu_baseline.json (profiles/tools/eager_gpu_baseline.py on a B200 of this pool: "
+                           "the reference algorithm as eager torch/cuDNN fp32 ops, cudnn.benchmark, TF32 off)"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(task), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"BCD X3D-L train (fwd+BCEDiceLoss+bwd+Adam), synthetic LEVIR-shape {S}x{S}, "
-                                       f"batch {B}/GPU, T=3", "global_batch": world * B, "parallelism": f"dp{world}",
+                "config": {"workload": f"{T['what']} {S}x{S}, batch {B}/GPU, T={T['P'] + 2}", "task": task,
+                           "baseline_config_index": T["cfg"], "global_batch": world * B, "parallelism": f"dp{world}",
                            "gemm_arithmetic": "3xTF32 split products on tcgen05, fp32 accumulate (fp32-class)",
                            "cuda_graph": not args.no_graph, "wgrad_side_stream": os.environ.get("C3D_SIDE_STREAM", "1") == "1",
                            "l2": "per-step working set (tens of GB of activations) >> 126 MB L2; no flush needed"},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "steps": k2, "input_staging": e2e_mode,
                         "all_modes": {k: round(v, 2) for k, v in e2e_runs.items()}},
-                "gpu_launches": launches_per_step, "loss": round(loss_val, 5), "clocks": sampler.summary(),
-                "metrics_on_device": {"confusion_matrix": cm_host, "pixels": int(sum(map(sum, cm_host))),
-                                      "note": "hist[target][output > 0.5] accumulated by the loss kernel, no per-step D2H"}}
+                "gpu_launches": launches_per_step, "loss": round(loss_val, 5), "clocks": sampler.summary()}
+        if cm_host is not None:
+            line["metrics_on_device"] = {"confusion_matrix": cm_host, "pixels": int(sum(map(sum, cm_host))),
+                                         "note": "hist[target][output > 0.5] accumulated by the loss kernel, no per-step D2H"}
         if roofline is not None:
             line["roofline"] = roofline
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity_256"] = parity
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         barrier()                                 # the other ranks wait here while rank 0 runs its probe

@@ -51,6 +51,6 @@ extern "C" int c3d_adam_step(float* p, const float* g, float* m, float* v, long 
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, step_size, inv_sqrt_bc2, beta1, beta2,
-                                                                   eps, weight_decay, grad_scale, grad_clip > 0.f ? grad_clip : __int_as_float(0x7f800000));
+                                                                   eps, weight_decay, grad_scale, grad_clip > 0.f ? grad_clip : HUGE_VALF);
   return c3d_check_last(cudaGetLastError());
 }

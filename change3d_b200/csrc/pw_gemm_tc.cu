@@ -869,7 +869,7 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   }
   P.pf_dist = 0;
   if (P.tma) {
-    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : -1;      // -1 auto, 0 off, n tiles
+    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : 0;       // 0 off (default: measured 1-4 % slower, profiles/r02_summary.md), -1 auto, n tiles
     const bool has2 = (g.a.mode == PRO_BNBWD || g.a.mode == PRO_ABSDIFF || g.a.mode == PRO_MASK_POS);
     const long long tile_bytes = (long long)tc::BM * g.a.K * 4 * (has2 ? 2 : 1);
     int d = (int)((128 * 1024 + tile_bytes - 1) / tile_bytes);

@@ -393,7 +393,7 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   P.nstage = nstage;
   const size_t smem = (size_t)nstage * P.stage_bytes + tail;
   {
-    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : -1;      // -1 auto, 0 off, n stages past the ring
+    static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : 0;       // 0 off (default), -1 auto, n stages past the ring
     auto two = [](const TileSrc& s) { return s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS; };
     const long long raw = (long long)PT * 128 * (P.Gb * (two(P.big) ? 2 : 1) + P.Gs * (two(P.small) ? 2 : 1));
     int d = (int)((128 * 1024 + raw - 1) / raw);

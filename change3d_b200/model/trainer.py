@@ -20,11 +20,28 @@ from .utils import weight_init
 from .x3d import create_x3d, _as_ncdhw_view, _as_ndhwc
 
 
+def _merge_slice_grads(g, gs, like: torch.Tensor, P: int) -> torch.Tensor:
+    """Gradient w.r.t. a published (B,C,T,H,W) feature tensor from its two consumers: `g` from the next stage (dense NDHWC
+    once permuted, or None) and `gs[k]` from the decoder head that read perception frame k+1 (or None).  The frame
+    gradients are added in place into the owned full-size gradient — one strided add per head instead of autograd's
+    zero-filled full-size tensor + slice copy + full-size add per slice (2.4 GB of traffic at the stem's resolution)."""
+    if g is None:
+        g = torch.zeros(like.shape, device=like.device, dtype=torch.float32)       # (B,T,H,W,C): last stage only
+    else:
+        g = engine.owned_ndhwc(g)
+    for k, gk in enumerate(gs):
+        if gk is not None:
+            g[:, k + 1].add_(gk.permute(0, 2, 3, 1))
+    return g
+
+
 class _StemEnhFn(torch.autograd.Function):
-    """blocks[0] on [pre, perception, post] + enhance, one autograd node."""
+    """blocks[0] on [pre, perception, post] + enhance, one autograd node.  Outputs: the (B,C,T,H,W) feature tensor and,
+    when `n_slices` > 0, its perception-frame slices f[:, :, k+1] as separate outputs (views of the same memory) so
+    that their gradients arrive separately (see _merge_slice_grads)."""
 
     @staticmethod
-    def forward(ctx, pre, post, perc, stem, fc_w, P, grad_on, w_xy, w_t, gamma, beta):
+    def forward(ctx, pre, post, perc, stem, fc_w, P, n_slices, grad_on, w_xy, w_t, gamma, beta):
         B, _, H, W = pre.shape
         pre = pre.contiguous()
         post = post.contiguous()
@@ -40,22 +57,24 @@ class _StemEnhFn(torch.autograd.Function):
             mid_pre = engine.enhance_forward(out, fc_w, P, need)
         ctx.stem, ctx.saved, ctx.frames, ctx.mid_pre, ctx.fc_w, ctx.P = stem, saved, frames, mid_pre, fc_w, P
         ctx.keep = (pre, post, percc)
-        return _as_ncdhw_view(out)
+        ctx.set_materialize_grads(False)
+        f = _as_ncdhw_view(out)
+        return (f,) + tuple(f[:, :, k + 1] for k in range(n_slices))
 
     @staticmethod
-    def backward(ctx, g):
-        g = engine.owned_ndhwc(g)
+    def backward(ctx, g, *gs):
         y, bnp, out = ctx.saved
+        g = _merge_slice_grads(g, gs, out, ctx.P)
         dfc = None
         if ctx.fc_w is not None:
             dfc = engine.enhance_backward(out, ctx.mid_pre, ctx.fc_w, ctx.P, g)
         dperc, dwxy, dwt, dgamma, dbeta = engine.stem_backward(ctx.stem, ctx.frames, y, bnp, out, g, ctx.P)
         ctx.saved = None
-        return None, None, dperc, None, dfc, None, None, dwxy, dwt, dgamma, dbeta
+        return None, None, dperc, None, dfc, None, None, None, dwxy, dwt, dgamma, dbeta
 
 
 class _StageEnhFn(torch.autograd.Function):
-    """blocks[i] (ResStage) + enhance, one autograd node."""
+    """blocks[i] (ResStage) + enhance, one autograd node; outputs as in _StemEnhFn."""
 
     @staticmethod
     def forward(ctx, x, stage, fc_w, P, grad_on, *params):
@@ -65,11 +84,13 @@ class _StageEnhFn(torch.autograd.Function):
         out, saved = engine.res_stage_forward(stage, _as_ndhwc(x), stage.training, need)
         mid_pre = engine.enhance_forward(out, fc_w, P, need)
         ctx.stage, ctx.saved, ctx.mid_pre, ctx.fc_w, ctx.P, ctx.out = stage, saved, mid_pre, fc_w, P, out
-        return _as_ncdhw_view(out)
+        ctx.set_materialize_grads(False)
+        f = _as_ncdhw_view(out)
+        return (f,) + tuple(f[:, :, k + 1] for k in range(P))
 
     @staticmethod
-    def backward(ctx, g):
-        g = engine.owned_ndhwc(g)
+    def backward(ctx, g, *gs):
+        g = _merge_slice_grads(g, gs, ctx.out, ctx.P)
         dfc = engine.enhance_backward(ctx.out, ctx.mid_pre, ctx.fc_w, ctx.P, g)
         dx, grads = engine.res_stage_backward(ctx.stage, ctx.saved, g)
         ctx.saved = None
@@ -109,16 +130,16 @@ class Encoder(nn.Module):
         grad_on = torch.is_grad_enabled()
         stem_args = (grad_on, stem.conv.conv_t.weight, stem.conv.conv_xy.weight, stem.norm.weight, stem.norm.bias)
         if output_final:                                                   # model/trainer.py:120-124
-            f = _StemEnhFn.apply(x.float(), y.float(), self.perception_frames, stem, None, P, *stem_args)
+            f = _StemEnhFn.apply(x.float(), y.float(), self.perception_frames, stem, None, P, 0, *stem_args)[0]
             for i in range(1, 5):
                 f = blocks[i](f)
             return f[:, :, P]
         out = []
-        f = _StemEnhFn.apply(x.float(), y.float(), self.perception_frames, stem, self.fc[0][0].weight, P, *stem_args)
-        out.append([f[:, :, k + 1] for k in range(P)])
+        res = _StemEnhFn.apply(x.float(), y.float(), self.perception_frames, stem, self.fc[0][0].weight, P, P, *stem_args)
+        out.append(list(res[1:]))
         for i in range(1, 4):                                              # model/trainer.py:127-139
-            f = _StageEnhFn.apply(f, blocks[i], self.fc[i][0].weight, P, grad_on, *blocks[i].param_list())
-            out.append([f[:, :, k + 1] for k in range(P)])
+            res = _StageEnhFn.apply(res[0], blocks[i], self.fc[i][0].weight, P, grad_on, *blocks[i].param_list())
+            out.append(list(res[1:]))
         return out
 
 

@@ -26,8 +26,13 @@ PROF = None
 
 
 class _Timed:
-    def __init__(self, family: str, nbytes: int):
+    """nbytes: every operand tensor of the fused design touched once; nbytes_model: the per-layer byte model of
+    SURVEY.md section 8(d) (a conv reads its input once and writes its output once, + weights; BN / activation /
+    residual operands are free) — what bench.py's `roofline.frac` is computed from.  Equal unless stated."""
+
+    def __init__(self, family: str, nbytes: int, nbytes_model: Optional[int] = None):
         self.family, self.nbytes = family, nbytes
+        self.nbytes_model = nbytes if nbytes_model is None else nbytes_model
 
     def __enter__(self):
         if PROF is not None:
@@ -39,7 +44,7 @@ class _Timed:
     def __exit__(self, *exc):
         if PROF is not None:
             self.e1.record()
-            PROF.setdefault(self.family, []).append((self.e0, self.e1, self.nbytes))
+            PROF.setdefault(self.family, []).append((self.e0, self.e1, self.nbytes, self.nbytes_model))
         return False
 
 
@@ -100,7 +105,7 @@ def pw_gemm(a: L.Operand, W: torch.Tensor, *, w_sr: int, w_so: int, Kred: int, N
     d.flags = L.GEMM_W_CONSTANT if isinstance(W, torch.nn.Parameter) else 0
     ka = a.ld * (a.nseg if a.nseg else (4 if a.map == MAP_CONVT_FWD else 16 if a.map == MAP_CONVT_BWD else 1))
     nbytes = 4 * (M * ka * (2 if a.A2 else 1) + M * Ns * (1 + (1 if E1 is not None else 0)) + Kred * N)
-    with _Timed("pw_gemm", nbytes):
+    with _Timed("pw_gemm", nbytes, 4 * (M * Kred + M * N + Kred * N)):
         L.check(L.load().c3d_pw_gemm(C.byref(d), _stream()), "c3d_pw_gemm")
 
 
@@ -110,7 +115,7 @@ def pw_wgrad(p: L.Operand, q: L.Operand, *, M: int, dW: torch.Tensor, dw_sn: int
     d.p = p; d.q = q; d.M = M; d.dW = _ptr(dW); d.dw_sn = dw_sn; d.dw_sk = dw_sk; d.N = N; d.K = K
     kq = q.ld * (q.nseg if q.nseg else (16 if q.map == MAP_CONVT_BWD else 1))
     nbytes = 4 * (M * p.ld * (2 if p.A2 else 1) + M * kq * (2 if q.A2 else 1) + N * K)
-    with _Timed("pw_wgrad", nbytes):
+    with _Timed("pw_wgrad", nbytes, 4 * (M * N + M * K + N * K)):
         L.check(L.load().c3d_pw_wgrad(C.byref(d), _stream()), "c3d_pw_wgrad")
 
 

@@ -37,4 +37,4 @@ torch.cuda.synchronize()
 if a.time:
     prof, ops.PROF = ops.PROF, None
     for fam, recs in prof.items():
-        print(fam, " ".join(f"{e0.elapsed_time(e1)*1e3:.0f}" for e0, e1, _ in recs))
+        print(fam, " ".join(f"{r[0].elapsed_time(r[1])*1e3:.0f}" for r in recs))
