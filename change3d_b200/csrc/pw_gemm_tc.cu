@@ -170,6 +170,26 @@ __device__ __forceinline__ void transform_chunk(const Params& P, const TileSrc& 
   const bool slow_gate = (MODE == PRO_BN_GATE_SWISH && s.gate && !gate_fast);
   // batches of 4 row groups: all shared-memory loads of a batch are issued before its first store (the in-place
   // stores would otherwise order every load behind the previous iteration's stores)
+  if (nvalid == BM && !slow_gate && gsplit >= BM) {
+    // common case: a full tile inside one batch sample -- no per-row selects (gate choice, tail zeroing) in the loop
+#pragma unroll 2
+    for (int b0 = bg0; b0 < bg1; b0 += 4) {
+      float4 v[4], v2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = *reinterpret_cast<const float4*>(a_hi + (b0 + i) * 128 + po);
+        v2[i] = HAS2 ? *reinterpret_cast<const float4*>(a_lo + (b0 + i) * 128 + po) : f4zero();
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        split4(prologue<MODE>(cp, v[i], v2[i], g0), hi, lo);
+        *reinterpret_cast<float4*>(a_hi + (b0 + i) * 128 + po) = hi;
+        *reinterpret_cast<float4*>(a_lo + (b0 + i) * 128 + po) = lo;
+      }
+    }
+    return;
+  }
 #pragma unroll 2
   for (int b0 = bg0; b0 < bg1; b0 += 4) {
     float4 v[4], v2[4];
@@ -564,6 +584,35 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
             // per-lane partial sums of (du, du * zhat) for the warp's first sample (a0, z0) and, when its 32 rows
             // straddle a sample boundary, the next one (a1, z1)
             float4 a0 = f4zero(), z0 = f4zero(), a1 = f4zero(), z1 = f4zero();
+            if (wsplit >= 32 && wrow0 + 32 <= g.M) {
+              // common case: the warp's 32 rows are all valid and belong to one sample -- no per-row predicates
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                E1_TAKE(i, yb)
+                const float4 acc = vv[i];
+                float4 du, dz;
+                {
+                  const float xc = yb.x - mean.x, u = fmaf(xc, scale.x, beta.x) * gt0.x;
+                  du.x = acc.x * swish_gradf_(u); dz.x = du.x * (xc * rstd.x);
+                }
+                {
+                  const float xc = yb.y - mean.y, u = fmaf(xc, scale.y, beta.y) * gt0.y;
+                  du.y = acc.y * swish_gradf_(u); dz.y = du.y * (xc * rstd.y);
+                }
+                {
+                  const float xc = yb.z - mean.z, u = fmaf(xc, scale.z, beta.z) * gt0.z;
+                  du.z = acc.z * swish_gradf_(u); dz.z = du.z * (xc * rstd.z);
+                }
+                {
+                  const float xc = yb.w - mean.w, u = fmaf(xc, scale.w, beta.w) * gt0.w;
+                  du.w = acc.w * swish_gradf_(u); dz.w = du.w * (xc * rstd.w);
+                }
+                if (col_ok) {
+                  st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, du);
+                  a0 = f4add(a0, du); z0 = f4add(z0, dz);
+                }
+              }
+            } else
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + (lane >> 3);

@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace tcm {
@@ -56,6 +58,51 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)1 << 61;       // layout_type SWIZZLE_128B_BASE32B
   return d;
+}
+
+// The rows of one job with everything per-channel / per-sample already in registers (the producer loop hoists them:
+// a warp's first job is the same (operand, channel group, 16-row chunk) in every stage).  FULL: all PT rows valid and
+// inside one batch sample -- no per-row selects.
+template <int MODE, bool FULL>
+__device__ __forceinline__ void transform_rows(const ChanParams& cp, float4 g0, float4 g1, int gsplit, int nvalid, bool kvalid,
+                                               float* hi, float* lo, int lane, int q0) {
+  constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
+  const int u = lane & 7, rsub = lane >> 3;
+  int o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 4 * (q0 + i) + rsub;
+    o[i] = r * 32 + (((((u >> 1) ^ (r & 3)) << 1) | (u & 1)) << 2);
+  }
+  if (!kvalid) {      // channels past K: TMA zero-filled the raw tile, the split halves must both read as zero
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(hi + o[i]) = f4zero();
+      *reinterpret_cast<float4*>(lo + o[i]) = f4zero();
+    }
+    return;
+  }
+  float4 v[4], v2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(hi + o[i]);
+    v2[i] = HAS2 ? *reinterpret_cast<const float4*>(lo + o[i]) : f4zero();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 x;
+    if (FULL) {
+      x = prologue<MODE>(cp, v[i], v2[i], g0);
+    } else {
+      const int r = 4 * (q0 + i) + rsub;
+      x = prologue<MODE>(cp, v[i], v2[i], (r >= gsplit) ? g1 : g0);
+      if (r >= nvalid) x = f4zero();
+    }
+    float4 h, l;
+    split4(x, h, l);
+    *reinterpret_cast<float4*>(hi + o[i]) = h;
+    *reinterpret_cast<float4*>(lo + o[i]) = l;
+  }
 }
 
 // In-place prologue + hi/lo split of one (operand, channel group) job: PT rows of 128 bytes, 16-byte unit u of row r
@@ -175,30 +222,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
     const int pw = warp - 4;
     const int nrc = P.PT / 16;                       // 16-row chunks per channel group
     const int njobs = (P.Gb + P.Gs) * nrc;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      DBG_T(d_a, mbar_wait(smem_u32(rawfull + stage), phase));
-      ++d_n;
-      const long long t_x = dbg_on ? clock64() : 0;
-      const long long row0 = (t_begin + ti) * P.PT;
-      float* st = reinterpret_cast<float*>(base + (size_t)stage * P.stage_bytes);
-      for (int job = pw; job < njobs; job += NPW) {
-        const int grp = job / nrc, q0 = (job - grp * nrc) * 4;      // (operand, channel group), 16-row chunk
-        if (grp < P.Gb) {
-          float* hi = st + (size_t)grp * (P.grp_bytes >> 2);
-          transform_group_any(P.big, P.M, row0, P.PT, grp, hi, hi + (P.off_blo >> 2), lane, q0);
-        } else {
-          const int g = grp - P.Gb;
-          float* hi = st + (P.off_shi >> 2) + (size_t)g * (P.grp_bytes >> 2);
-          transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane, q0);
-        }
+    // A warp's first job (job index pw) is the same (operand, channel group, row chunk) in every stage: its channel
+    // parameters are loaded once, and the SE gate of the current batch sample is tracked incrementally (the tiles of
+    // a CTA are consecutive rows), so the per-stage work is the four row quads themselves.  Further jobs of the warp
+    // (more than 12 jobs per stage: 432-channel layers) take the generic path.
+    const bool has0 = pw < njobs;
+    const int grp0 = has0 ? pw / nrc : 0, q00 = has0 ? (pw - grp0 * nrc) * 4 : 0;
+    const bool big0 = grp0 < P.Gb;
+    const TileSrc& s0 = big0 ? P.big : P.small;
+    const int g_0 = big0 ? grp0 : grp0 - P.Gb;
+    const uint32_t hi_off0 = big0 ? (uint32_t)g_0 * (P.grp_bytes >> 2) : (P.off_shi >> 2) + (uint32_t)g_0 * (P.grp_bytes >> 2);
+    const uint32_t lo_rel0 = big0 ? (P.off_blo >> 2) : ((P.off_slo - P.off_shi) >> 2);
+    int k0 = g_0 * 32 + 4 * (lane & 7);
+    const bool kvalid0 = k0 < s0.K;
+    if (!kvalid0) k0 = 0;
+    const uint32_t rps0 = (uint32_t)s0.OHW * (uint32_t)s0.frames_per_sample;
+    const bool gated0 = s0.mode == PRO_BN_GATE_SWISH && s0.gate != nullptr;
+    const bool hoist0 = has0 && (!gated0 || rps0 >= (uint32_t)P.PT);
+    auto run = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      const ChanParams cp = hoist0 ? load_chan_params<MODE>(s0, k0) : ChanParams();
+      const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 g0 = ones, g1 = ones;
+      uint32_t samp = 0, samp_end = 0xffffffffu;       // first row of the next batch sample (no gate: never reached)
+      if (hoist0 && gated0 && my_tiles > 0) {
+        const uint32_t r0 = (uint32_t)(t_begin * P.PT);
+        samp = r0 / rps0;
+        samp_end = (samp + 1) * rps0;
+        g0 = ldg4(s0.gate + (long long)samp * s0.ld + k0);
       }
-      if (dbg_on) d_c += clock64() - t_x;
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(full + stage));
-      if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        DBG_T(d_a, mbar_wait(smem_u32(rawfull + stage), phase));
+        ++d_n;
+        const long long t_x = dbg_on ? clock64() : 0;
+        const long long row0 = (t_begin + ti) * P.PT;
+        float* st = reinterpret_cast<float*>(base + (size_t)stage * P.stage_bytes);
+        if (hoist0) {
+          int gsplit = P.PT;
+          if (gated0) {
+            while ((uint32_t)row0 >= samp_end) { ++samp; samp_end += rps0; g0 = ldg4(s0.gate + (long long)samp * s0.ld + k0); }
+            if (samp_end - (uint32_t)row0 < (uint32_t)P.PT) {
+              gsplit = (int)(samp_end - (uint32_t)row0);
+              g1 = (long long)samp_end < P.M ? ldg4(s0.gate + (long long)(samp + 1) * s0.ld + k0) : ones;
+            }
+          }
+          const long long left = P.M - row0;
+          const int nvalid = left < P.PT ? (int)left : P.PT;
+          float* hi = st + hi_off0;
+          if (nvalid == P.PT && gsplit >= P.PT) transform_rows<MODE, true>(cp, g0, g1, gsplit, nvalid, kvalid0, hi, hi + lo_rel0, lane, q00);
+          else transform_rows<MODE, false>(cp, g0, g1, gsplit, nvalid, kvalid0, hi, hi + lo_rel0, lane, q00);
+        }
+        for (int job = hoist0 ? pw + NPW : pw; job < njobs; job += NPW) {
+          const int grp = job / nrc, q0 = (job - grp * nrc) * 4;      // (operand, channel group), 16-row chunk
+          if (grp < P.Gb) {
+            float* hi = st + (size_t)grp * (P.grp_bytes >> 2);
+            transform_group_any(P.big, P.M, row0, P.PT, grp, hi, hi + (P.off_blo >> 2), lane, q0);
+          } else {
+            const int g = grp - P.Gb;
+            float* hi = st + (P.off_shi >> 2) + (size_t)g * (P.grp_bytes >> 2);
+            transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane, q0);
+          }
+        }
+        if (dbg_on) d_c += clock64() - t_x;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(full + stage));
+        if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+      }
+    };
+    switch (s0.mode) {
+      case PRO_NONE: run(std::integral_constant<int, PRO_NONE>()); break;
+      case PRO_BN_RELU: run(std::integral_constant<int, PRO_BN_RELU>()); break;
+      case PRO_BN_GATE_SWISH: run(std::integral_constant<int, PRO_BN_GATE_SWISH>()); break;
+      case PRO_BNBWD: run(std::integral_constant<int, PRO_BNBWD>()); break;
+      case PRO_ABSDIFF: run(std::integral_constant<int, PRO_ABSDIFF>()); break;
+      default: run(std::integral_constant<int, PRO_MASK_POS>()); break;
     }
   } else {
     // ===================== TMA issuer: epilogue warp 1 (idle until the end) =====================
@@ -278,22 +378,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
     }
     __syncwarp();
     // ===================== final epilogue: lane = big channel, columns = small channels =====================
+    // A warp's 32 x 32 block is added to dW with 32-lane contiguous atomics either way round: directly when the big
+    // channel index is the contiguous one (dw_sb == 1), through a transposing pass over shared memory when the small
+    // one is (dw_ss == 1: lane-strided atomics cost one L2 transaction per lane -- 63 K cycles of a 143 K-cycle launch
+    // for the 216 x 96 conv_a gradient).  The pipeline stages are free by now (every MMA has retired).
     if (my_tiles > 0) {
       DBG_T(d_a, mbar_wait(smem_u32(done), 0));
       tc_fence_after();
+      float* S = reinterpret_cast<float*>(base) + warp * (32 * 33);
+      const bool transpose = P.dw_ss == 1 && P.dw_sb != 1;
       for (int b = 0; b < P.nblocks; ++b) {
-        const int bc = b * 128 + warp * 32 + lane;          // big channel index of this thread
+        const int bc0 = b * 128 + warp * 32;                // first big channel of this warp's lanes
+        const int bc = bc0 + lane;
         const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * P.NsP);
         for (int c0 = 0; c0 < P.NsP; c0 += 32) {
           float r[32], r2[32];
           tmem_ld32(t_main + (uint32_t)c0, r);
           tmem_ld32(t_main + (uint32_t)(P.NsP + c0), r2);
-          if (bc < P.Nb) {
+          if (!transpose) {
+            if (bc < P.Nb) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int sc = c0 + j;
-              if (sc < P.Ns_) atomicAdd(P.dW + (long long)bc * P.dw_sb + (long long)sc * P.dw_ss, r[j] + r2[j]);
+              for (int j = 0; j < 32; ++j) {
+                const int sc = c0 + j;
+                if (sc < P.Ns_) atomicAdd(P.dW + (long long)bc * P.dw_sb + (long long)sc * P.dw_ss, r[j] + r2[j]);
+              }
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) S[lane * 33 + j] = r[j] + r2[j];
+            __syncwarp();
+            const int sc = c0 + lane;
+            if (sc < P.Ns_) {
+              const int nrow = P.Nb - bc0 < 32 ? P.Nb - bc0 : 32;
+              for (int rr = 0; rr < nrow; ++rr) atomicAdd(P.dW + (long long)(bc0 + rr) * P.dw_sb + sc, S[rr * 33 + lane]);
+            }
+            __syncwarp();
           }
         }
       }

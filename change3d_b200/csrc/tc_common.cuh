@@ -137,7 +137,9 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
   split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
 }
 
-// prologue applied to one float4 of 4 consecutive channels; per-channel parameters are passed in registers
+// prologue applied to one float4 of 4 consecutive channels; per-channel parameters are passed in registers.
+// PRO_BNBWD keeps folded constants: scale * (v - c1 - (y - mean) * rstd * c2) = fma(y - mean, k2, fma(v, scale, k0)) with
+// k0 = -c1 * scale (stored in c1) and k2 = -rstd * c2 * scale (stored in c2): 3 instructions per element instead of 6.
 struct ChanParams { float4 mean, rstd, scale, beta, c1, c2; };
 
 template <int MODE>
@@ -151,8 +153,10 @@ __device__ __forceinline__ ChanParams load_chan_params(const TileSrc& s, int c) 
   if (MODE == PRO_BN_RELU || MODE == PRO_BN_GATE_SWISH) p.beta = ldg4(BNP_BETA(s.bnp, s.ld) + c);
   if (MODE == PRO_BNBWD) {
     p.rstd = ldg4(BNP_RSTD(s.bnp, s.ld) + c);
-    p.c1 = ldg4(s.coef + c);
-    p.c2 = ldg4(s.coef + s.ld + c);
+    const float4 c1 = ldg4(s.coef + c), c2 = ldg4(s.coef + s.ld + c);
+    p.c1 = make_float4(-c1.x * p.scale.x, -c1.y * p.scale.y, -c1.z * p.scale.z, -c1.w * p.scale.w);
+    p.c2 = make_float4(-p.rstd.x * c2.x * p.scale.x, -p.rstd.y * c2.y * p.scale.y, -p.rstd.z * c2.z * p.scale.z,
+                       -p.rstd.w * c2.w * p.scale.w);
   }
   return p;
 }
@@ -166,10 +170,10 @@ __device__ __forceinline__ float4 prologue(const ChanParams& p, float4 v, float4
     return make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
   }
   if (MODE == PRO_BNBWD) {
-    v.x = p.scale.x * (v.x - p.c1.x - (v2.x - p.mean.x) * p.rstd.x * p.c2.x);
-    v.y = p.scale.y * (v.y - p.c1.y - (v2.y - p.mean.y) * p.rstd.y * p.c2.y);
-    v.z = p.scale.z * (v.z - p.c1.z - (v2.z - p.mean.z) * p.rstd.z * p.c2.z);
-    v.w = p.scale.w * (v.w - p.c1.w - (v2.w - p.mean.w) * p.rstd.w * p.c2.w);
+    v.x = fmaf(v2.x - p.mean.x, p.c2.x, fmaf(v.x, p.scale.x, p.c1.x));
+    v.y = fmaf(v2.y - p.mean.y, p.c2.y, fmaf(v.y, p.scale.y, p.c1.y));
+    v.z = fmaf(v2.z - p.mean.z, p.c2.z, fmaf(v.z, p.scale.z, p.c1.z));
+    v.w = fmaf(v2.w - p.mean.w, p.c2.w, fmaf(v.w, p.scale.w, p.c1.w));
     return v;
   }
   if (MODE == PRO_ABSDIFF) return make_float4(fabsf(v.x - v2.x), fabsf(v.y - v2.y), fabsf(v.z - v2.z), fabsf(v.w - v2.w));

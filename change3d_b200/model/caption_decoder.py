@@ -108,7 +108,10 @@ class CaptionDecoder(nn.Module):
         L = tgt.size(0)
         mask = torch.full((L, L), float('-inf'), device=tgt.device).triu(diagonal=1)
         emb = self.position_encoding(self.vocab_embedding(tgt))
-        pred = self.transformer(emb, memory, tgt_mask=mask)
+        # tgt_is_causal=False: nn.TransformerDecoder otherwise inspects the mask on the host (`.all()` read-back per
+        # call — a device synchronisation, and illegal while a CUDA graph is being captured); the layers receive the
+        # explicit mask either way and ignore the hint
+        pred = self.transformer(emb, memory, tgt_mask=mask, tgt_is_causal=False)
         pred = self.wdc(self.dropout_layer(pred)).permute(1, 0, 2)
         caption_lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
         return pred[sort_ind], encoded_captions[sort_ind], caption_lengths - 1, sort_ind

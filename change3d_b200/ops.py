@@ -7,6 +7,7 @@ Activations are fp32 NDHWC torch tensors of shape (N, T, H, W, Cs).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -49,8 +50,15 @@ class _Timed:
 
 
 def pad8(c: int) -> int:
-    """Channel stride of the bottleneck's inner tensors (54->56, 108->112, 216, 432)."""
-    return (c + 7) // 8 * 8
+    """Channel stride of the bottleneck's inner tensors: a multiple of 8 (54->56, 108->112, 432), and of 16 floats
+    (64 bytes, the DRAM access granularity) where that costs under 5 % (216->224): with a 864-byte pixel stride every
+    second pixel's 128-byte channel block starts mid-atom and the depthwise kernels, which read one channel block
+    per CTA, fetch 1.25x their bytes from HBM (profiles/r02_summary.md).  C3D_PAD16=0 keeps the multiple of 8."""
+    c8 = (c + 7) // 8 * 8
+    c16 = (c + 15) // 16 * 16
+    if c16 != c8 and (c16 - c) * 20 <= c and os.environ.get("C3D_PAD16", "1") == "1":
+        return c16
+    return c8
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
