@@ -65,14 +65,17 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Off by default: measured on B200 at batch 32 the step is 2.3 % SLOWER with it (64.19 vs 62.72 ms, same box,
 // profiles/r01_summary.md section 5) -- the early-resident CTAs of the next kernel compete with the weight-gradient
 // GEMMs that already fill the dependency bubbles from the side stream.  C3D_PDL=1 turns it on (read per launch).
-static inline bool c3d_pdl_enabled() {
+// C3D_PDL=2: only the single-CTA finalizer kernels (BN / SE statistics -> parameters) are launched that way: they become
+// resident while their producer is still running (the producers trigger early) and only pay their own latency after it.
+static inline int c3d_pdl_mode() {
   const char* v = getenv("C3D_PDL");
-  return v && atoi(v) != 0;
+  return v ? atoi(v) : 0;
 }
+static inline bool c3d_pdl_enabled() { return c3d_pdl_mode() == 1; }
 
 template <typename... KArgs, typename... Args>
-static inline cudaError_t c3d_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                         Args&&... args) {
+static inline cudaError_t c3d_launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                            Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -82,8 +85,19 @@ static inline cudaError_t c3d_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = c3d_pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = on ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t c3d_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args&&... args) {
+  return c3d_launch_pdl_if(c3d_pdl_mode() == 1, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+// finalizer kernels (one or a few tiny CTAs between two grid-filling kernels)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t c3d_launch_pdl_small(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                               Args&&... args) {
+  return c3d_launch_pdl_if(c3d_pdl_mode() >= 1, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 // Operand descriptor for the pointwise-GEMM family (see pw_gemm.cu).

@@ -11,11 +11,21 @@ __device__ __forceinline__ void bn_params_for_channel(const double* stats, int g
                                                       bool write_running, float& mean_f, float& rstd_f) {
   double mean, var;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int g = 0; g < groups; ++g) {
+    // four independent partial sums per moment: the loads of the batch loop are issued together instead of one
+    // L2 round trip per sample (the loop is the latency of this single-wave kernel)
+    double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
+    int g = 0;
+    for (; g + 4 <= groups; g += 4) {
+      const double* p = stats + ((long long)g * 2) * Cs + c;
+      const double a0 = p[0], b0 = p[Cs], a1 = p[2 * Cs], b1 = p[3 * Cs], a2 = p[4 * Cs], b2 = p[5 * Cs], a3 = p[6 * Cs], b3 = p[7 * Cs];
+      s += a0; q += b0; s1 += a1; q1 += b1; s2 += a2; q2 += b2; s3 += a3; q3 += b3;
+    }
+    for (; g < groups; ++g) {
       s += stats[((long long)g * 2 + 0) * Cs + c];
       q += stats[((long long)g * 2 + 1) * Cs + c];
     }
+    s += s1 + s2 + s3;
+    q += q1 + q2 + q3;
     mean = s / (double)count;
     var = q / (double)count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -54,7 +64,7 @@ extern "C" int c3d_bn_finalize(const double* stats, int groups, long long count,
                                int training, float* bnp, void* stream_) {
   if (!gamma || !beta || !bnp || C <= 0 || Cs < C) return C3D_ERR_ARG;
   if (training ? (!stats || groups <= 0 || count <= 0) : (!running_mean || !running_var)) return C3D_ERR_ARG;
-  c3d_launch_pdl(bn_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, gamma, beta, running_mean,
+  c3d_launch_pdl_small(bn_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, gamma, beta, running_mean,
                                                             running_var, C, Cs, momentum, eps, training, bnp);
   return c3d_check_last(cudaGetLastError());
 }
@@ -123,7 +133,7 @@ extern "C" int c3d_bn_se_finalize(const double* stats, int N, long long count_pe
   if (!training && (!running_mean || !running_var)) return C3D_ERR_ARG;
   if (w1 && (!b1 || !w2 || !b2 || R <= 0 || !hidden || !gate)) return C3D_ERR_ARG;
   size_t smem = (size_t)(Cs + (R > 0 ? R : 0)) * sizeof(float);
-  c3d_launch_pdl(bn_se_finalize_kernel, dim3(N), dim3(256), smem, (cudaStream_t)stream_, stats, N, count_per_sample, gamma, beta, running_mean,
+  c3d_launch_pdl_small(bn_se_finalize_kernel, dim3(N), dim3(256), smem, (cudaStream_t)stream_, stats, N, count_per_sample, gamma, beta, running_mean,
                                                                  running_var, C, Cs, momentum, eps, training, w1, b1,
                                                                  w2, b2, R, bnp, zhat_mean, hidden, gate);
   return c3d_check_last(cudaGetLastError());
@@ -258,11 +268,14 @@ __global__ void bn_bwd_finalize_kernel(const double* stats, int groups, long lon
 extern "C" int c3d_bn_bwd_finalize(const double* stats, int groups, long long count, int C, int Cs, float* coef,
                                    float* dgamma, float* dbeta, void* stream_) {
   if (!stats || !coef || !dgamma || !dbeta || groups <= 0 || count <= 0 || C <= 0 || Cs < C) return C3D_ERR_ARG;
-  c3d_launch_pdl(bn_bwd_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, C, Cs, coef, dgamma, dbeta);
+  c3d_launch_pdl_small(bn_bwd_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream_, stats, groups, count, C, Cs, coef, dgamma, dbeta);
   return c3d_check_last(cudaGetLastError());
 }
 
 // SE backward + BN_b backward coefficients.  stats = double[N][2][Cs]: per-sample (sum du, sum du*zhat).
+// One CTA (the work is ~0.5 MFLOP); every phase is laid out so that no thread walks the batch with dependent global
+// loads: the per-sample inputs are staged in shared memory once, sums over the batch run on (channel, quarter of the
+// batch) threads and are folded through shared memory.
 __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     const double* __restrict__ stats, int N, long long cnt, const float* __restrict__ bnp, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ gate, const float* __restrict__ hidden,
@@ -272,12 +285,16 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
   pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
   pdl_wait();      // then wait for the earlier kernels whose results this one reads
 
-  extern __shared__ float sm[];
-  float* dps = sm;               // [N][C]   grad wrt pre-sigmoid
-  float* dpr = sm + (size_t)N * C;   // [N][R]   grad wrt pre-relu
+  extern __shared__ double smd[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const bool se = (gate != nullptr);
   const double Mtot = (double)cnt * (double)N;
+  // shared: part[4][2][C] doubles | dps[N][C] | dpr[N][R] | hid[N][R] | pin[N][C] (SE only)
+  double* part = smd;                                   // [4][2][C]
+  float* dps = reinterpret_cast<float*>(part + 8 * C);  // [N][C]   grad wrt pre-sigmoid
+  float* dpr = dps + (size_t)N * C;                     // [N][R]   grad wrt pre-relu
+  float* hid = dpr + (size_t)N * R;                     // [N][R]   relu output of fc1 (forward)
+  float* pin = hid + (size_t)N * R;                     // [N][C]   fc1 input: gamma * zhat_mean + beta
   if (se) {
     for (int i = tid; i < N * C; i += nthr) {
       const int n = i / C, c = i - n * C;
@@ -285,7 +302,9 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
       const float g = gate[(long long)n * Cs + c];
       const float dg = (float)((double)gamma[c] * Bz + (double)beta[c] * A);   // sum du * z
       dps[i] = dg * g * (1.f - g);
+      pin[i] = fmaf(zhat_mean[(long long)n * Cs + c], gamma[c], beta[c]);
     }
+    for (int i = tid; i < N * R; i += nthr) hid[i] = hidden[i];
     __syncthreads();
     for (int c = tid; c < C; c += nthr) {
       float s = 0.f;
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     for (int i = tid; i < C * R; i += nthr) {
       const int c = i / R, r = i - c * R;
       float s = 0.f;
-      for (int n = 0; n < N; ++n) s = fmaf(dps[n * C + c], hidden[(long long)n * R + r], s);
+      for (int n = 0; n < N; ++n) s = fmaf(dps[n * C + c], hid[n * R + r], s);
       dw2[i] = s;
     }
     const int warp = tid >> 5, lane = tid & 31;
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
       for (int c = lane; c < C; c += 32) s = fmaf(w2[c * R + r], dps[n * C + c], s);
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) dpr[i] = hidden[(long long)n * R + r] > 0.f ? s : 0.f;
+      if (lane == 0) dpr[i] = hid[i] > 0.f ? s : 0.f;
     }
     __syncthreads();
     for (int r = tid; r < R; r += nthr) {
@@ -316,26 +335,37 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     for (int i = tid; i < R * C; i += nthr) {
       const int r = i / C, c = i - r * C;
       float s = 0.f;
-      for (int n = 0; n < N; ++n) s = fmaf(dpr[n * R + r], fmaf(zhat_mean[(long long)n * Cs + c], gamma[c], beta[c]), s);
+      for (int n = 0; n < N; ++n) s = fmaf(dpr[n * R + r], pin[n * C + c], s);
       dw1[i] = s;
     }
   }
+  // batch sums S1 = sum_n (g A + dp), S2 = sum_n (g Bz + dp zm): thread = (channel, quarter of the batch)
+  for (int i = tid; i < 4 * C; i += nthr) {
+    const int qn = i / C, c = i - qn * C;
+    const int n0 = qn * ((N + 3) >> 2), n1 = n0 + ((N + 3) >> 2) < N ? n0 + ((N + 3) >> 2) : N;
+    double S1 = 0.0, S2 = 0.0;
+    for (int n = n0; n < n1; ++n) {
+      const double A = stats[((long long)n * 2) * Cs + c], Bz = stats[((long long)n * 2 + 1) * Cs + c];
+      if (se) {
+        float dp = 0.f;
+        for (int r = 0; r < R; ++r) dp = fmaf(w1[r * C + c], dpr[n * R + r], dp);
+        const double g = (double)gate[(long long)n * Cs + c];
+        S1 += g * A + (double)dp;
+        S2 += g * Bz + (double)dp * (double)zhat_mean[(long long)n * Cs + c];
+        dpool[(long long)n * Cs + c] = (float)((double)dp / (double)cnt);
+      } else {
+        S1 += A; S2 += Bz;
+      }
+    }
+    part[(qn * 2 + 0) * C + c] = S1;
+    part[(qn * 2 + 1) * C + c] = S2;
+  }
+  __syncthreads();
   for (int c = tid; c < Cs; c += nthr) {
     double S1 = 0.0, S2 = 0.0;
     if (c < C) {
-      for (int n = 0; n < N; ++n) {
-        const double A = stats[((long long)n * 2) * Cs + c], Bz = stats[((long long)n * 2 + 1) * Cs + c];
-        if (se) {
-          float dp = 0.f;
-          for (int r = 0; r < R; ++r) dp = fmaf(w1[r * C + c], dpr[n * R + r], dp);
-          const double g = (double)gate[(long long)n * Cs + c];
-          S1 += g * A + (double)dp;
-          S2 += g * Bz + (double)dp * (double)zhat_mean[(long long)n * Cs + c];
-          dpool[(long long)n * Cs + c] = (float)((double)dp / (double)cnt);
-        } else {
-          S1 += A; S2 += Bz;
-        }
-      }
+      S1 = part[c] + part[2 * C + c] + part[4 * C + c] + part[6 * C + c];
+      S2 = part[C + c] + part[3 * C + c] + part[5 * C + c] + part[7 * C + c];
       dgamma[c] = (float)S2;
       dbeta[c] = (float)S1;
     } else if (se) {
@@ -354,10 +384,10 @@ extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long coun
   if (!stats || !bnp || !gamma || !beta || !coef || !dgamma || !dbeta || N <= 0 || count_per_sample <= 0 || C <= 0 || Cs < C)
     return C3D_ERR_ARG;
   if (gate && (!hidden || !zhat_mean || !w1 || !w2 || !dpool || !dw1 || !db1 || !dw2 || !db2 || R <= 0)) return C3D_ERR_ARG;
-  size_t smem = gate ? ((size_t)N * C + (size_t)N * R) * sizeof(float) : 0;
+  size_t smem = (size_t)8 * C * sizeof(double) + (gate ? ((size_t)2 * N * C + (size_t)2 * N * R) * sizeof(float) : 0);
   if (smem > 200 * 1024) return C3D_ERR_SMEM;
   cudaFuncSetAttribute(se_bn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  c3d_launch_pdl(se_bn_bwd_finalize_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream_, stats, N, count_per_sample, bnp, gamma, beta, gate,
+  c3d_launch_pdl_small(se_bn_bwd_finalize_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream_, stats, N, count_per_sample, bnp, gamma, beta, gate,
                                                                     hidden, zhat_mean, w1, w2, C, Cs, R, coef, dgamma,
                                                                     dbeta, dpool, dw1, db1, dw2, db2);
   return c3d_check_last(cudaGetLastError());

@@ -131,10 +131,11 @@ def bn_finalize(stats: Optional[torch.Tensor], groups: int, count: int, bn: torc
                 training: bool) -> torch.Tensor:
     """stats -> bnp float[4][Cs]; updates bn.running_* in training (nn.BatchNorm3d semantics)."""
     bnp = torch.empty(4 * Cs, device=bn.weight.device, dtype=torch.float32)
-    L.check(L.load().c3d_bn_finalize(_ptr(stats), groups, count, _ptr(bn.weight), _ptr(bn.bias),
-                                     _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
-                                     bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
-                                     1 if training else 0, _ptr(bnp), _stream()), "c3d_bn_finalize")
+    with _Timed("bn_finalize", 0):
+        L.check(L.load().c3d_bn_finalize(_ptr(stats), groups, count, _ptr(bn.weight), _ptr(bn.bias),
+                                         _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
+                                         bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
+                                         1 if training else 0, _ptr(bnp), _stream()), "c3d_bn_finalize")
     return bnp
 
 
@@ -153,12 +154,13 @@ def bn_se_finalize(stats: torch.Tensor, N: int, count_per_sample: int, bn: torch
     else:
         w1 = b1 = w2 = b2 = hidden = gate = None
         R = 0
-    L.check(L.load().c3d_bn_se_finalize(_ptr(stats), N, count_per_sample, _ptr(bn.weight), _ptr(bn.bias),
-                                        _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
-                                        bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
-                                        1 if training else 0, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), R,
-                                        _ptr(bnp), _ptr(zhat_mean), _ptr(hidden), _ptr(gate), _stream()),
-            "c3d_bn_se_finalize")
+    with _Timed("bn_se_finalize", 0):
+        L.check(L.load().c3d_bn_se_finalize(_ptr(stats), N, count_per_sample, _ptr(bn.weight), _ptr(bn.bias),
+                                            _ptr(bn.running_mean), _ptr(bn.running_var), C_, Cs,
+                                            bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps,
+                                            1 if training else 0, _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), R,
+                                            _ptr(bnp), _ptr(zhat_mean), _ptr(hidden), _ptr(gate), _stream()),
+                "c3d_bn_se_finalize")
     return bnp, zhat_mean, hidden, gate
 
 
@@ -224,8 +226,9 @@ def relu_bwd_stats(dOut, out, y_c, bnp_c, y_1, bnp_1, stats_c, stats_1) -> torch
 
 def bn_bwd_finalize(stats, groups: int, count: int, C_: int, Cs: int, dgamma: torch.Tensor, dbeta: torch.Tensor):
     coef = torch.empty(2 * Cs, device=stats.device, dtype=torch.float32)
-    L.check(L.load().c3d_bn_bwd_finalize(_ptr(stats), groups, count, C_, Cs, _ptr(coef), _ptr(dgamma), _ptr(dbeta),
-                                         _stream()), "c3d_bn_bwd_finalize")
+    with _Timed("bn_bwd_finalize", 0):
+        L.check(L.load().c3d_bn_bwd_finalize(_ptr(stats), groups, count, C_, Cs, _ptr(coef), _ptr(dgamma), _ptr(dbeta),
+                                             _stream()), "c3d_bn_bwd_finalize")
     return coef
 
 
@@ -242,10 +245,12 @@ def se_bn_bwd_finalize(stats, N: int, count_per_sample: int, bnp, bn, se, gate, 
         w1 = w2 = dpool = dw1 = db1 = dw2 = db2 = None
         gate = hidden = zhat_mean = None
         R = 0
-    L.check(L.load().c3d_se_bn_bwd_finalize(_ptr(stats), N, count_per_sample, _ptr(bnp), _ptr(bn.weight), _ptr(bn.bias),
-                                            _ptr(gate), _ptr(hidden), _ptr(zhat_mean), _ptr(w1), _ptr(w2), C_, Cs, R,
-                                            _ptr(coef), _ptr(dgamma), _ptr(dbeta), _ptr(dpool), _ptr(dw1), _ptr(db1),
-                                            _ptr(dw2), _ptr(db2), _stream()), "c3d_se_bn_bwd_finalize")
+    with _Timed("se_bn_bwd_finalize", 0):
+        L.check(L.load().c3d_se_bn_bwd_finalize(_ptr(stats), N, count_per_sample, _ptr(bnp), _ptr(bn.weight),
+                                                _ptr(bn.bias), _ptr(gate), _ptr(hidden), _ptr(zhat_mean), _ptr(w1),
+                                                _ptr(w2), C_, Cs, R, _ptr(coef), _ptr(dgamma), _ptr(dbeta), _ptr(dpool),
+                                                _ptr(dw1), _ptr(db1), _ptr(dw2), _ptr(db2), _stream()),
+                "c3d_se_bn_bwd_finalize")
     return coef, dpool
 
 
