@@ -2,6 +2,8 @@
 // gate, the fused residual join, and their backward counterparts.
 // Reference: nn.BatchNorm3d sites model/x3d.py:94-98,176-180,203-208,217-221,296-298; fvcore
 // SqueezeExcitation call site model/x3d.py:194-202; ResBlock fusion model/x3d.py:326-327.
+#include <stdio.h>
+#include <stdlib.h>
 #include "c3d_common.cuh"
 #include "../../include/change3d_b200.h"
 
@@ -15,6 +17,14 @@ __device__ __forceinline__ void bn_params_for_channel(const double* stats, int g
     // L2 round trip per sample (the loop is the latency of this single-wave kernel)
     double s = 0.0, q = 0.0, s1 = 0.0, q1 = 0.0, s2 = 0.0, q2 = 0.0, s3 = 0.0, q3 = 0.0;
     int g = 0;
+    for (; g + 8 <= groups; g += 8) {      // 16 loads in flight
+      const double* p = stats + ((long long)g * 2) * Cs + c;
+      double a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a[u] = p[(2 * u) * Cs]; b[u] = p[(2 * u + 1) * Cs]; }
+      s += a[0] + a[4]; q += b[0] + b[4]; s1 += a[1] + a[5]; q1 += b[1] + b[5];
+      s2 += a[2] + a[6]; q2 += b[2] + b[6]; s3 += a[3] + a[7]; q3 += b[3] + b[7];
+    }
     for (; g + 4 <= groups; g += 4) {
       const double* p = stats + ((long long)g * 2) * Cs + c;
       const double a0 = p[0], b0 = p[Cs], a1 = p[2 * Cs], b1 = p[3 * Cs], a2 = p[4 * Cs], b2 = p[5 * Cs], a3 = p[6 * Cs], b3 = p[7 * Cs];
@@ -101,9 +111,17 @@ __global__ void __launch_bounds__(256) bn_se_finalize_kernel(
   if (!w1) return;   // BN only
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // fc1: one warp per hidden unit; the weight loads of a row are issued in batches of 8 (the loop is otherwise one L2
+  // round trip per 32 channels), and the rows a warp handles are independent
   for (int r = warp; r < R; r += 8) {
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[r * C + c], pooled[c], s);
+    for (int c0 = 0; c0 < C; c0 += 256) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; wv[u] = c < C ? __ldg(w1 + r * C + c) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; if (c < C) s = fmaf(wv[u], pooled[c], s); }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
@@ -117,7 +135,20 @@ __global__ void __launch_bounds__(256) bn_se_finalize_kernel(
     float g = 0.f;
     if (c < C) {
       float s = b2[c];
-      for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
+      if ((R & 3) == 0 && R <= 32 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0) {      // a channel's fc2 row is R contiguous floats: vector loads, all in flight
+        float4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = 4 * u < R ? ldg4(w2 + c * R + 4 * u) : f4zero();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (4 * u < R) {
+            s = fmaf(wv[u].x, hid[4 * u], s); s = fmaf(wv[u].y, hid[4 * u + 1], s);
+            s = fmaf(wv[u].z, hid[4 * u + 2], s); s = fmaf(wv[u].w, hid[4 * u + 3], s);
+          }
+        }
+      } else {
+        for (int r = 0; r < R; ++r) s = fmaf(w2[c * R + r], hid[r], s);
+      }
       g = sigmoidf_(s);
     }
     gate[(long long)n * Cs + c] = g;
@@ -281,9 +312,12 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     const float* __restrict__ beta, const float* __restrict__ gate, const float* __restrict__ hidden,
     const float* __restrict__ zhat_mean, const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cs, int R,
     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dpool,
-    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2) {
+    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
+    long long* __restrict__ dbg) {
   pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
   pdl_wait();      // then wait for the earlier kernels whose results this one reads
+#define FIN_T(k) do { if (dbg && threadIdx.x == 0) dbg[k] = clock64(); } while (0)
+  FIN_T(0);
 
   extern __shared__ double smd[];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -306,6 +340,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     }
     for (int i = tid; i < N * R; i += nthr) hid[i] = hidden[i];
     __syncthreads();
+    FIN_T(1);
     for (int c = tid; c < C; c += nthr) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += dps[n * C + c];
@@ -317,6 +352,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
       for (int n = 0; n < N; ++n) s = fmaf(dps[n * C + c], hid[n * R + r], s);
       dw2[i] = s;
     }
+    FIN_T(2);
     const int warp = tid >> 5, lane = tid & 31;
     for (int i = warp; i < N * R; i += (nthr >> 5)) {
       const int n = i / R, r = i - n * R;
@@ -327,6 +363,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
       if (lane == 0) dpr[i] = hid[i] > 0.f ? s : 0.f;
     }
     __syncthreads();
+    FIN_T(3);
     for (int r = tid; r < R; r += nthr) {
       float s = 0.f;
       for (int n = 0; n < N; ++n) s += dpr[n * R + r];
@@ -338,6 +375,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
       for (int n = 0; n < N; ++n) s = fmaf(dpr[n * R + r], pin[n * C + c], s);
       dw1[i] = s;
     }
+    FIN_T(4);
   }
   // batch sums S1 = sum_n (g A + dp), S2 = sum_n (g Bz + dp zm): thread = (channel, quarter of the batch)
   for (int i = tid; i < 4 * C; i += nthr) {
@@ -361,6 +399,7 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     part[(qn * 2 + 1) * C + c] = S2;
   }
   __syncthreads();
+  FIN_T(5);
   for (int c = tid; c < Cs; c += nthr) {
     double S1 = 0.0, S2 = 0.0;
     if (c < C) {
@@ -374,6 +413,164 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_finalize_kernel(
     coef[c] = (float)(S1 / Mtot);
     coef[Cs + c] = (float)(S2 / Mtot);
   }
+  FIN_T(6);
+#undef FIN_T
+}
+
+// Latency-lean version of the SE case (the one above spends 60 us, almost all of it in loops whose every iteration is a
+// dependent global load: 66 K cycles in the fc2-transpose phase alone, profiles/r02_summary.md).  Same arithmetic, but
+//   * thread (channel c, batch group j) owns the samples n = j, j + G, ...: their per-sample sums (fp64), gate and zhat
+//     mean are loaded ONCE, all loads in flight together, and stay in registers for the final batch sums;
+//   * fc1 / fc2 weights and the hidden activations are staged in shared memory by coalesced loads in the same phase;
+//   * every later phase reads shared memory only; the fc2-transpose runs on (sample, r, H-way split of the channels)
+//     threads with a shuffle fold.
+// IPT = samples per thread (compile-time bound of the register arrays).
+template <int IPT>
+__global__ void __launch_bounds__(1024) se_bn_bwd_fast_kernel(
+    const double* __restrict__ stats, int N, long long cnt, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ gate, const float* __restrict__ hidden, const float* __restrict__ zhat_mean,
+    const float* __restrict__ w1, const float* __restrict__ w2, int C, int Cs, int R, int G, int H,
+    float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dpool,
+    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2,
+    long long* __restrict__ dbg) {
+  pdl_trigger();
+  pdl_wait();
+#define FIN_T(k) do { if (dbg && threadIdx.x == 0) dbg[k] = clock64(); } while (0)
+  FIN_T(0);
+  extern __shared__ double smd[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  double* part = smd;                                       // [G][2][C]
+  float* dps = reinterpret_cast<float*>(part + (size_t)G * 2 * C);   // [N][C] grad wrt the pre-sigmoid fc2 output
+  float* pin = dps + (size_t)N * C;                         // [N][C] fc1 input: gamma * zhat_mean + beta
+  float* hid = pin + (size_t)N * C;                         // [N][R] relu output of fc1 (forward)
+  float* dpr = hid + (size_t)N * R;                         // [N][R] grad wrt the pre-relu fc1 output
+  float* w1s = dpr + (size_t)N * R;                         // [R][C]
+  float* w2s = w1s + (size_t)R * C;                         // [C][R]
+  const int j = tid / C, c = tid - j * C;
+  const bool active = j < G;
+  double A[IPT], Bz[IPT];
+  float gt[IPT], zm[IPT];
+  float gam = 0.f, bet = 0.f;
+  if (active) {
+    gam = gamma[c]; bet = beta[c];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const int n = j + k * G;
+      A[k] = 0.0; Bz[k] = 0.0; gt[k] = 0.f; zm[k] = 0.f;
+      if (n < N) {
+        A[k] = stats[((long long)n * 2) * Cs + c];
+        Bz[k] = stats[((long long)n * 2 + 1) * Cs + c];
+        gt[k] = gate[(long long)n * Cs + c];
+        zm[k] = zhat_mean[(long long)n * Cs + c];
+      }
+    }
+  }
+  for (int i = tid; i < N * R; i += nthr) hid[i] = hidden[i];
+  for (int i = tid; i < R * C; i += nthr) { w1s[i] = w1[i]; w2s[i] = w2[i]; }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const int n = j + k * G;
+      if (n < N) {
+        const float dg = (float)((double)gam * Bz[k] + (double)bet * A[k]);   // sum du * z
+        dps[n * C + c] = dg * gt[k] * (1.f - gt[k]);
+        pin[n * C + c] = fmaf(zm[k], gam, bet);
+      }
+    }
+  }
+  __syncthreads();
+  FIN_T(1);
+  // ---- fc2 backward: bias / weight gradients and the gradient of the hidden activations ----
+  for (int cc = tid; cc < C; cc += nthr) {
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) { s0 += dps[n * C + cc]; s1 += dps[(n + 1) * C + cc]; }
+    if (n < N) s0 += dps[n * C + cc];
+    db2[cc] = s0 + s1;
+  }
+  for (int i = tid; i < C * R; i += nthr) {
+    const int cc = i / R, r = i - cc * R;
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      s0 = fmaf(dps[n * C + cc], hid[n * R + r], s0);
+      s1 = fmaf(dps[(n + 1) * C + cc], hid[(n + 1) * R + r], s1);
+    }
+    if (n < N) s0 = fmaf(dps[n * C + cc], hid[n * R + r], s0);
+    dw2[i] = s0 + s1;
+  }
+  FIN_T(2);
+  {
+    const int h = tid & (H - 1);
+    for (int base = 0; base < N * R; base += nthr / H) {      // block-uniform trip count: every lane reaches the shuffles
+      const int o = base + tid / H;
+      const bool ok = o < N * R;
+      const int n = ok ? o / R : 0, r = ok ? o - n * R : 0;
+      float s0 = 0.f, s1 = 0.f;
+      int cc = h;
+      for (; cc + H < C; cc += 2 * H) {
+        s0 = fmaf(w2s[cc * R + r], dps[n * C + cc], s0);
+        s1 = fmaf(w2s[(cc + H) * R + r], dps[n * C + cc + H], s1);
+      }
+      if (cc < C) s0 = fmaf(w2s[cc * R + r], dps[n * C + cc], s0);
+      float sres = s0 + s1;
+      for (int of = H >> 1; of; of >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, of);
+      if (ok && h == 0) dpr[o] = hid[o] > 0.f ? sres : 0.f;
+    }
+  }
+  __syncthreads();
+  FIN_T(3);
+  // ---- fc1 backward + batch sums of this thread's own samples ----
+  for (int r = tid; r < R; r += nthr) {
+    float sres = 0.f;
+    for (int n = 0; n < N; ++n) sres += dpr[n * R + r];
+    db1[r] = sres;
+  }
+  for (int i = tid; i < R * C; i += nthr) {
+    const int r = i / C, cc = i - r * C;
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      s0 = fmaf(dpr[n * R + r], pin[n * C + cc], s0);
+      s1 = fmaf(dpr[(n + 1) * R + r], pin[(n + 1) * C + cc], s1);
+    }
+    if (n < N) s0 = fmaf(dpr[n * R + r], pin[n * C + cc], s0);
+    dw1[i] = s0 + s1;
+  }
+  FIN_T(4);
+  if (active) {
+    double S1 = 0.0, S2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const int n = j + k * G;
+      if (n < N) {
+        float dp = 0.f;
+        for (int r = 0; r < R; ++r) dp = fmaf(w1s[r * C + c], dpr[n * R + r], dp);
+        S1 += (double)gt[k] * A[k] + (double)dp;
+        S2 += (double)gt[k] * Bz[k] + (double)dp * (double)zm[k];
+        dpool[(long long)n * Cs + c] = (float)((double)dp / (double)cnt);
+      }
+    }
+    part[(j * 2 + 0) * C + c] = S1;
+    part[(j * 2 + 1) * C + c] = S2;
+  }
+  __syncthreads();
+  FIN_T(5);
+  const double Mtot = (double)cnt * (double)N;
+  for (int cc = tid; cc < Cs; cc += nthr) {
+    double S1 = 0.0, S2 = 0.0;
+    if (cc < C) {
+      for (int g = 0; g < G; ++g) { S1 += part[(g * 2 + 0) * C + cc]; S2 += part[(g * 2 + 1) * C + cc]; }
+      dgamma[cc] = (float)S2;
+      dbeta[cc] = (float)S1;
+    } else {
+      for (int n = 0; n < N; ++n) dpool[(long long)n * Cs + cc] = 0.f;
+    }
+    coef[cc] = (float)(S1 / Mtot);
+    coef[Cs + cc] = (float)(S2 / Mtot);
+  }
+  FIN_T(6);
+#undef FIN_T
 }
 
 extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long count_per_sample, const float* bnp,
@@ -384,12 +581,41 @@ extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long coun
   if (!stats || !bnp || !gamma || !beta || !coef || !dgamma || !dbeta || N <= 0 || count_per_sample <= 0 || C <= 0 || Cs < C)
     return C3D_ERR_ARG;
   if (gate && (!hidden || !zhat_mean || !w1 || !w2 || !dpool || !dw1 || !db1 || !dw2 || !db2 || R <= 0)) return C3D_ERR_ARG;
+  static const bool dbg_on = getenv("C3D_FIN_DBG") && atoi(getenv("C3D_FIN_DBG")) != 0;
+  static long long* dbuf = nullptr;
+  if (dbg_on && !dbuf) cudaMalloc(&dbuf, 8 * sizeof(long long));
+  auto report = [&](const char* which) {      // bring-up aid (synchronising): cycles per phase of the single CTA
+    long long h[8];
+    cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_);
+    cudaStreamSynchronize((cudaStream_t)stream_);
+    fprintf(stderr, "[findbg] %s se=%d N=%d C=%d R=%d p0=%lld p1=%lld p2=%lld p3=%lld p4=%lld p5=%lld\n", which, gate != nullptr, N, C, R,
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+  };
+  static const bool fast_on = !(getenv("C3D_FIN_FAST") && atoi(getenv("C3D_FIN_FAST")) == 0);
+  if (gate && fast_on && C <= 1024 && R <= 64) {
+    int G = 1024 / C;
+    if (G > N) G = N;
+    const int ipt = (N + G - 1) / G;
+    int H = 1;
+    while (2 * H * N * R <= 1024 && 2 * H <= 32) H *= 2;
+    const size_t fsmem = (size_t)G * 2 * C * sizeof(double) + ((size_t)2 * N * C + (size_t)2 * N * R + (size_t)2 * R * C) * sizeof(float);
+    if (ipt <= 8 && fsmem <= 220 * 1024) {
+      auto kern = ipt <= 2 ? se_bn_bwd_fast_kernel<2> : ipt <= 4 ? se_bn_bwd_fast_kernel<4> : se_bn_bwd_fast_kernel<8>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem) != cudaSuccess) return C3D_ERR_SMEM;
+      c3d_launch_pdl_small(kern, dim3(1), dim3(1024), fsmem, (cudaStream_t)stream_, stats, N, count_per_sample, gamma, beta, gate, hidden,
+                           zhat_mean, w1, w2, C, Cs, R, G, H, coef, dgamma, dbeta, dpool, dw1, db1, dw2, db2,
+                           dbg_on ? dbuf : (long long*)nullptr);
+      if (dbg_on) report("fast");
+      return c3d_check_last(cudaGetLastError());
+    }
+  }
   size_t smem = (size_t)8 * C * sizeof(double) + (gate ? ((size_t)2 * N * C + (size_t)2 * N * R) * sizeof(float) : 0);
   if (smem > 200 * 1024) return C3D_ERR_SMEM;
   cudaFuncSetAttribute(se_bn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   c3d_launch_pdl_small(se_bn_bwd_finalize_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream_, stats, N, count_per_sample, bnp, gamma, beta, gate,
                                                                     hidden, zhat_mean, w1, w2, C, Cs, R, coef, dgamma,
-                                                                    dbeta, dpool, dw1, db1, dw2, db2);
+                                                                    dbeta, dpool, dw1, db1, dw2, db2, dbg_on ? dbuf : (long long*)nullptr);
+  if (dbg_on) report("slow");
   return c3d_check_last(cudaGetLastError());
 }
 

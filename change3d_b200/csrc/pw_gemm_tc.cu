@@ -47,6 +47,8 @@ struct Params {
   int dense_contig;  // rows are contiguous pixels: offset = row * ld
   int lbo_is_k;      // descriptor convention switch (1: LBO = stride between K chunks)
   int wait_hint;     // mbarrier try_wait suspend hint in ns (0 = none)
+  int ncat;          // 1: W hi / W lo column groups are interleaved per K chunk so that Ah x [Wh | Wl] is ONE MMA of 2 * NpB
+                     // columns writing [main | correction] (correction at column NpB): A hi is read twice, not three times
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
   int pf_dist;       // TMA path: L2 prefetch distance in tiles (0 = off): the boxes of tile t + pf_dist are requested
                      // when tile t's copies are issued, so HBM latency is paid ahead of the shared-memory pipeline
@@ -238,8 +240,8 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
 
   // ---- shared memory carve-up ----
   float* B_hi = reinterpret_cast<float*>(smem_raw);                 // [K/4][NpB/8][8][4]
-  float* B_lo = B_hi + (size_t)NpB * K;
-  float* stages = B_lo + (size_t)NpB * K;                           // nstage x (A_hi, A_lo)
+  float* B_lo = P.ncat ? B_hi + (size_t)NpB * 4 : B_hi + (size_t)NpB * K;   // ncat: [K/4][hi: NpB/8 | lo: NpB/8][8][4]
+  float* stages = B_hi + (size_t)2 * NpB * K;                       // nstage x (A_hi, A_lo)
   float* epi = stages + (size_t)P.nstage * 2 * STAGE_FLOATS;        // NEPI warps x epi_bufs x [32][EPI_LD]
   float* s_stat = epi + NEPI * P.epi_bufs * 32 * EPI_LD;            // [NEPI warps][2][NpA]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + NEPI * 2 * P.NpA);
@@ -262,27 +264,61 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
   // Programmatic dependent launch: everything up to here touches no global memory.  Model parameters are constant
   // within a step, so their staging below may also overlap the previous kernel's tail; other weights wait first.
   if (!g.w_const) pdl_wait();
+  const long long d_tw0 = dbg_on ? clock64() : 0;
   // resident weights, split and laid out for UMMA (zero outside the logical matrix)
   {
-    const int kq4 = K >> 2;
+    // Batches of WU quads per thread with every global load of a batch issued before the first split / store: the
+    // staging is L2-latency bound (a handful of dependent round trips per thread used to cost ~9-12 K cycles per
+    // launch, profiles/r02_summary.md), so the loads of a batch must be in flight together.
+    const uint32_t kq4 = (uint32_t)K >> 2;
+    const uint32_t total = (uint32_t)NpB * kq4;
     const float* Wg = g.W;
-    for (int idx = threadIdx.x; idx < NpB * kq4; idx += NTHREADS) {
-      int n, q;
-      if (g.w_sr == 1) { n = idx / kq4; q = idx - n * kq4; } else { q = idx / NpB; n = idx - q * NpB; }
-      float w[4];
+    const bool k_contig = g.w_sr == 1;
+    const bool vec_ok = k_contig && (g.w_so & 3) == 0 && (g.Kred & 3) == 0 && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
+    constexpr int WU = 4;
+    for (uint32_t base = threadIdx.x; base < total; base += NTHREADS * WU) {
+      float4 wv[WU];
+      int oo[WU];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int red = 4 * q + j;
-        w[j] = (red < g.Kred && n0 + n < g.N) ? __ldg(Wg + (long long)red * g.w_sr + (long long)(n0 + n) * g.w_so) : 0.f;
+      for (int u = 0; u < WU; ++u) {
+        const uint32_t idx = base + (uint32_t)u * NTHREADS;
+        wv[u] = f4zero();
+        oo[u] = -1;
+        if (idx < total) {
+          uint32_t n, q;
+          // lanes = 8 consecutive columns x 4 consecutive K quads: the shared stores of a quarter warp then cover 128
+          // contiguous bytes (with K fastest all 32 lanes of a store hit one bank group -- a 32-way conflict that cost
+          // 8 K cycles per launch for the 112 x 96 block), and the global reads are still 64-byte runs per column
+          if (k_contig) { const uint32_t t = idx >> 3; const uint32_t nh = t / kq4; q = t - nh * kq4; n = nh * 8 + (idx & 7); }
+          else { q = idx / (uint32_t)NpB; n = idx - q * (uint32_t)NpB; }
+          oo[u] = (int)(((q * (uint32_t)((P.ncat ? 2 * NpB : NpB) >> 3) + (n >> 3)) * 8 + (n & 7)) * 4);
+          if ((int)(n0 + n) < g.N) {
+            const float* src = Wg + (long long)(4 * q) * g.w_sr + (long long)(n0 + n) * g.w_so;
+            if (vec_ok) {
+              if ((int)(4 * q) < g.Kred) wv[u] = ldg4(src);
+            } else {
+              const int red = (int)(4 * q);
+              if (red + 0 < g.Kred) wv[u].x = __ldg(src);
+              if (red + 1 < g.Kred) wv[u].y = __ldg(src + (long long)g.w_sr);
+              if (red + 2 < g.Kred) wv[u].z = __ldg(src + 2LL * g.w_sr);
+              if (red + 3 < g.Kred) wv[u].w = __ldg(src + 3LL * g.w_sr);
+            }
+          }
+        }
       }
-      float4 hi, lo;
-      split4(make_float4(w[0], w[1], w[2], w[3]), hi, lo);
-      const int o = ((q * (NpB >> 3) + (n >> 3)) * 8 + (n & 7)) * 4;
-      *reinterpret_cast<float4*>(B_hi + o) = hi;
-      *reinterpret_cast<float4*>(B_lo + o) = lo;
+#pragma unroll
+      for (int u = 0; u < WU; ++u) {
+        if (oo[u] >= 0) {
+          float4 hi, lo;
+          split4(wv[u], hi, lo);
+          *reinterpret_cast<float4*>(B_hi + oo[u]) = hi;
+          *reinterpret_cast<float4*>(B_lo + oo[u]) = lo;
+        }
+      }
     }
     for (int i = threadIdx.x; i < NEPI * 2 * P.NpA; i += NTHREADS) s_stat[i] = 0.f;
   }
+  const long long d_tw1 = dbg_on ? clock64() : 0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -392,7 +428,9 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
       const uint32_t leader = lane == 0 ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NpB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lboA = 16 * 128, sboA = 128;                       // stage layout [k-chunk][row group][8][16 B]
-      const uint32_t lboB = (uint32_t)(NpB >> 3) * 128, sboB = 128;     // weights     [k-chunk][col group][8][16 B]
+      const uint32_t lboB = (uint32_t)((P.ncat ? 2 * NpB : NpB) >> 3) * 128, sboB = 128;     // weights     [k-chunk][col group][8][16 B]
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NpB) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
       // descriptor templates with a zero start address; the address field (bits 0-13, 16-byte units) is added per use
       uint64_t tA, tB;
       uint32_t a_kstep;                                                  // byte offset of the second K step inside a stage half
@@ -411,7 +449,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
         ++d_n;
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)(set * 2 * P.NpA);
-        const uint32_t d_corr = d_main + (uint32_t)P.NpA;
+        const uint32_t d_corr = d_main + (uint32_t)(P.ncat ? NpB : P.NpA);
         uint64_t dbh = dB_hi0, dbl = dB_lo0;
         int kleft = K;
         uint32_t accum = 0;
@@ -422,12 +460,20 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
           const uint64_t dah = tA + (uint64_t)(ahi >> 4), dal = dah + (uint64_t)((STAGE_FLOATS * 4) >> 4);
           const uint32_t two = (leader && kleft >= KC) ? 1u : 0u;
           const uint64_t dah2 = dah + (a_kstep >> 4), dal2 = dal + (a_kstep >> 4), dbh2 = dbh + b_kstep16, dbl2 = dbl + b_kstep16;
-          umma_tf32_if(leader, d_main, dah, dbh, idesc, accum);
-          umma_tf32_if(leader, d_corr, dal, dbh, idesc, accum);
-          umma_tf32_if(leader, d_corr, dah, dbl, idesc, 1u);
-          umma_tf32_if(two, d_main, dah2, dbh2, idesc, 1u);
-          umma_tf32_if(two, d_corr, dal2, dbh2, idesc, 1u);
-          umma_tf32_if(two, d_corr, dah2, dbl2, idesc, 1u);
+          // folded: [main | corr] (+)= Ah x [Wh | Wl], corr += Al x Wh;  round-1 scheme: three products per K step
+          if (P.ncat) {
+            umma_tf32_if(leader, d_main, dah, dbh, idesc2, accum);
+            umma_tf32_if(leader, d_corr, dal, dbh, idesc, 1u);
+            umma_tf32_if(two, d_main, dah2, dbh2, idesc2, 1u);
+            umma_tf32_if(two, d_corr, dal2, dbh2, idesc, 1u);
+          } else {
+            umma_tf32_if(leader, d_main, dah, dbh, idesc, accum);
+            umma_tf32_if(leader, d_corr, dal, dbh, idesc, accum);
+            umma_tf32_if(leader, d_corr, dah, dbl, idesc, 1u);
+            umma_tf32_if(two, d_main, dah2, dbh2, idesc, 1u);
+            umma_tf32_if(two, d_corr, dal2, dbh2, idesc, 1u);
+            umma_tf32_if(two, d_corr, dah2, dbl2, idesc, 1u);
+          }
           umma_commit_if(leader, empty0 + (uint32_t)stage * 8);
           accum = 1u;
           dbh += 2 * b_kstep16; dbl += 2 * b_kstep16;
@@ -510,7 +556,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
       ++d_n;
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(set * 2 * P.NpA);
-      const uint32_t t_corr = t_main + (uint32_t)P.NpA;
+      const uint32_t t_corr = t_main + (uint32_t)(P.ncat ? NpB : P.NpA);
       for (int cc = 0; cc < ncc; ++cc) {
         {
           float r[32], r2[32];
@@ -533,21 +579,40 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
         const bool col_ok = col < g.Ns && cl < NpB;
         const long long tile_o = (wrow0 + (lane >> 3)) * (long long)g.Ns + col;
         if (g.epi == EPI_STORE) {
+          float4 sv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sv[i] = *reinterpret_cast<const float4*>(S + (4 * i + (lane >> 3)) * EPI_LD + 4 * q);
           if (col_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + (lane >> 3);
-              if (full_tile || row0 + wq * 32 + rr < g.M)
-                st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, *reinterpret_cast<const float4*>(S + rr * EPI_LD + 4 * q));
+              if (full_tile || row0 + wq * 32 + rr < g.M) st4(g.Y + tile_o + (long long)(4 * i) * g.Ns, sv[i]);
             }
           }
-          __syncwarp();
-          if (has_stats) {     // column sums straight from the staged tile (rows past M and pad columns hold zeros)
-            float t1 = 0.f, t2 = 0.f;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) { const float x = S[rr * EPI_LD + lane]; t1 += x; t2 = fmaf(x, x, t2); }
-            st[cc * 32 + lane] += t1;
-            st[P.NpA + cc * 32 + lane] += t2;
+          if (has_stats) {
+            // column sums from the quads already in registers (rows past M and pad columns hold zeros): 8 rows per
+            // lane, then the four lanes that share a column quad are folded -- no second pass over the staged tile
+            // (shared-memory bandwidth, not issue slots, is what these kernels run out of: profiles/r02_summary.md)
+            float4 t1 = f4zero(), t2 = f4zero();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              t1 = f4add(t1, sv[i]);
+              t2.x = fmaf(sv[i].x, sv[i].x, t2.x); t2.y = fmaf(sv[i].y, sv[i].y, t2.y);
+              t2.z = fmaf(sv[i].z, sv[i].z, t2.z); t2.w = fmaf(sv[i].w, sv[i].w, t2.w);
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              t1.x += __shfl_xor_sync(0xffffffffu, t1.x, o); t1.y += __shfl_xor_sync(0xffffffffu, t1.y, o);
+              t1.z += __shfl_xor_sync(0xffffffffu, t1.z, o); t1.w += __shfl_xor_sync(0xffffffffu, t1.w, o);
+              t2.x += __shfl_xor_sync(0xffffffffu, t2.x, o); t2.y += __shfl_xor_sync(0xffffffffu, t2.y, o);
+              t2.z += __shfl_xor_sync(0xffffffffu, t2.z, o); t2.w += __shfl_xor_sync(0xffffffffu, t2.w, o);
+            }
+            if (lane < 8) {
+              float4* s1 = reinterpret_cast<float4*>(st + cc * 32 + 4 * q);
+              float4* s2 = reinterpret_cast<float4*>(st + P.NpA + cc * 32 + 4 * q);
+              *s1 = f4add(*s1, t1);
+              *s2 = f4add(*s2, t2);
+            }
           }
         } else {
           float4 mean = f4zero(), rstd = f4zero(), scale = f4zero(), beta = f4zero();
@@ -799,7 +864,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
     const long long t_end = clock64();
     o[0] = (unsigned long long)(d_t1 - d_t0); o[1] = (unsigned long long)(t_end - d_t1);
     o[2] = (unsigned long long)d_a; o[3] = (unsigned long long)d_b; o[4] = (unsigned long long)d_c; o[5] = (unsigned long long)d_n;
-    o[6] = (unsigned long long)my_tiles; o[7] = (unsigned long long)nchunks;
+    o[6] = (unsigned long long)my_tiles; o[7] = (unsigned long long)(d_tw1 - d_tw0) | ((unsigned long long)(d_tw0 - d_t0) << 32);
   }
 #undef DBG_T
   tc_fence_before();
@@ -873,8 +938,8 @@ static int tc_launch(const tc::Params& P, const CUtensorMap& tmA, const CUtensor
     for (int w = 0; w < NEPI + 1 + NPROD; ++w) {
       const unsigned long long* o = h + w * 8;
       const char* role = w < NEPI ? "epi " : w == NEPI ? "mma " : "prod";
-      fprintf(stderr, "[tcdbg]  w%02d %s setup=%llu total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu chunks=%llu\n", w, role,
-              o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+      fprintf(stderr, "[tcdbg]  w%02d %s setup=%llu (pre %llu, weights %llu) total=%llu waitA=%llu waitB=%llu work=%llu n=%llu tiles=%llu\n", w, role,
+              o[0], o[7] >> 32, o[7] & 0xffffffffull, o[1], o[2], o[3], o[4], o[5], o[6]);
     }
     return c3d_check_last(cudaGetLastError());
   }
@@ -903,6 +968,10 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   P.lbo_is_k = lbo_is_k & 1;
   P.wait_hint = lbo_is_k >> 1;      // upper bits of the bring-up flag carry the wait hint (C3D_TC_HINT)
   P.epi_bufs = 1;
+  {
+    static const int cat_env = getenv("C3D_TC_CAT") ? atoi(getenv("C3D_TC_CAT")) : 1;
+    P.ncat = cat_env ? 1 : 0;
+  }
   P.dense_contig = (g.a.map == MAP_DENSE && g.a.img_stride == (long long)g.a.OHW * g.a.ld &&
                     (g.a.A2 == nullptr || g.a.img_stride2 == (long long)g.a.OHW * g.a.ld)) ? 1 : 0;
   // TMA feed: rows must be uniformly strided (dense map); the second operand shares the row geometry

@@ -41,6 +41,8 @@ struct Params {
   int tmem_cols;
   int swap_lbo;            // bring-up switch: exchange the LBO / SBO fields of the MN-major descriptors
   int pf_dist;             // L2 prefetch distance in stages (0 = off), counted from the stage being loaded
+  int ncat;                // 1: [S hi | S lo] is read as ONE operand of 2 * NsP columns (Bh x [Sh | Sl] in one MMA)
+  int stack;               // 1 (needs ncat, 2 * Gb <= 4): [B hi ; B lo] fills the 128 lanes, one MMA per k-step
   uint32_t stage_bytes, off_blo, off_shi, off_slo, grp_bytes;
   unsigned long long* dbg;
 };
@@ -346,6 +348,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       // M = 128 (big channels), N = NsP (small channels), K = 8 pixels; both operands MN-major
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.NsP >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
+      // The issue rate of these MMAs is bound by their shared-memory operand reads (MN-major TF32: ~140-170 cycles per
+      // M128 x N x K8 instruction measured, profiles/r02_summary.md), so the three split products are folded:
+      //   ncat : S hi and S lo are adjacent column groups -> Bh x [Sh | Sl] is ONE instruction of 2 * NsP columns that
+      //          writes [main | correction]; Bl x Sh then accumulates into the correction columns (2 reads of B, not 3)
+      //   stack: with <= 2 channel groups the 128 lanes hold [B hi ; B lo] (the layout that used to be padding), so the
+      //          same instruction also yields Bl x [Sh | Sl] in lanes 32 * Gb ..: one MMA per k-step, lanes folded by
+      //          the final atomics
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((2 * P.NsP) >> 3) << 17) |
+                              ((uint32_t)(128 >> 4) << 24);
+      const uint32_t ncat = P.ncat ? 1u : 0u, second = (P.ncat && !P.stack) ? 1u : 0u;
       const uint32_t lbo = P.swap_lbo ? 512u : P.grp_bytes, sbo = P.swap_lbo ? P.grp_bytes : 512u;
       const uint64_t tmpl = make_desc_mn128(0, lbo, sbo);      // start address (16-byte units, bits 0-13) is added per use
       const uint32_t blk16 = (4u * P.grp_bytes) >> 4;           // descriptor units between 128-channel blocks
@@ -364,9 +376,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
           for (int b = 0; b < P.nblocks; ++b) {
             const uint32_t db = tmem_base + (uint32_t)(b * 2 * P.NsP);
             const uint64_t bo = (uint64_t)((uint32_t)b * blk16);
-            umma_tf32_if(leader, db, dbh + bo, dsh, idesc, first);
-            umma_tf32_if(leader, db + (uint32_t)P.NsP, dbl + bo, dsh, idesc, first);
-            umma_tf32_if(leader, db + (uint32_t)P.NsP, dbh + bo, dsl, idesc, 1u);
+            if (ncat) {
+              umma_tf32_if(leader, db, dbh + bo, dsh, idesc2, first);
+              umma_tf32_if(leader & second, db + (uint32_t)P.NsP, dbl + bo, dsh, idesc, 1u);
+            } else {
+              umma_tf32_if(leader, db, dbh + bo, dsh, idesc, first);
+              umma_tf32_if(leader, db + (uint32_t)P.NsP, dbl + bo, dsh, idesc, first);
+              umma_tf32_if(leader, db + (uint32_t)P.NsP, dbh + bo, dsl, idesc, 1u);
+            }
           }
           first = 1u;
           dsh += 64; dsl += 64; dbh += 64; dbl += 64;           // next 8 pixels: two 512-byte atoms
@@ -388,7 +405,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       float* S = reinterpret_cast<float*>(base) + warp * (32 * 33);
       const bool transpose = P.dw_ss == 1 && P.dw_sb != 1;
       for (int b = 0; b < P.nblocks; ++b) {
-        const int bc0 = b * 128 + warp * 32;                // first big channel of this warp's lanes
+        // stacked operand: lanes 32 * Gb .. 64 * Gb hold the B-lo rows of channels 0 .. 32 * Gb (their products with
+        // [Sh | Sl] are added to the same dW entries by the atomics below); lanes past 64 * Gb hold nothing
+        if (P.stack && warp >= 2 * P.Gb) break;
+        const int bc0 = P.stack ? (warp >= P.Gb ? warp - P.Gb : warp) * 32 : b * 128 + warp * 32;   // first big channel of this warp's lanes
         const int bc = bc0 + lane;
         const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * P.NsP);
         for (int c0 = 0; c0 < P.NsP; c0 += 32) {
@@ -483,6 +503,11 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   P.nblocks = (P.Gb + 3) / 4;
   P.NsP = P.Gs * 32;
   if (P.NsP > 256 || P.nblocks > 4) return -1;
+  {      // C3D_WMN_CAT: 0 = three MMAs per k-step (round-1 scheme), 1 = folded split products without lane stacking, 2 (default) = both
+    static const int cat_env = getenv("C3D_WMN_CAT") ? atoi(getenv("C3D_WMN_CAT")) : 2;
+    P.ncat = (cat_env >= 1 && 2 * P.NsP <= 256) ? 1 : 0;
+    P.stack = (cat_env >= 2 && P.ncat && 2 * P.Gb <= 4) ? 1 : 0;
+  }
   int cols = 32;
   while (cols < P.nblocks * 2 * P.NsP) cols <<= 1;
   if (cols > 512) return -1;
