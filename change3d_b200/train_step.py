@@ -152,7 +152,9 @@ class TrainStep:
     The BCEDice kernel also accumulates the confusion matrix hist[target][output > 0.5] of the binary head into
     `self.cm` (int64 (2,2), device) — the per-step `eval_meter.update_cm(pred.cpu().numpy(), target.cpu().numpy())`
     of scripts/train_BCD.py:203-225 without leaving the GPU; read it with `scores()` at the end of an epoch.
-    `self.parts` holds the device scalars of the last iteration's loss terms (seg / binary / sim), as the scripts log."""
+    `self.parts` holds the device scalars of the last iteration's loss terms (seg / binary / sim), as the scripts log;
+    `self.outs` the heads' outputs of the last iteration (SCD / BDA: the scripts compute training accuracy from them).
+    Under the CUDA graph both live in the graph's memory pool and are overwritten by every replay."""
 
     def __init__(self, model, lr: float = 2e-4, use_graph: bool = False, task: str = "bcd"):
         if task not in ("bcd", "scd", "bda"):
@@ -163,6 +165,7 @@ class TrainStep:
         self.cm = torch.zeros(2, 2, dtype=torch.int64, device=self.opt.flat_p.device)
         self.sim = ChangeSimilarity()
         self.parts = {}
+        self.outs = ()
         self.use_graph = use_graph
         self.graph = None
         self.static = None
@@ -180,12 +183,14 @@ class TrainStep:
             binary = bce_dice_loss(change_mask, label_change.unsqueeze(1).float(), cm=self.cm)
             sim = self.sim(pre_mask[:, 1:], post_mask[:, 1:], label_change.unsqueeze(1))
             self.parts = {"seg": seg.detach(), "binary": binary.detach(), "sim": sim.detach()}
+            self.outs = (pre_mask.detach(), post_mask.detach(), change_mask.detach())
             return seg * 0.5 + binary + sim
         label_loc, label_cls = labels
         pred_cls, pred_loc = self.model.update_bda(pre, post)
         seg = cross_entropy_2d(pred_cls, label_cls, 0)
         binary = bce_dice_loss(pred_loc, label_loc.unsqueeze(1), cm=self.cm)
         self.parts = {"seg": seg.detach(), "binary": binary.detach()}
+        self.outs = (pred_cls.detach(), pred_loc.detach())
         return seg + binary
 
     def _iteration(self, pre, post, *labels) -> torch.Tensor:
