@@ -13,8 +13,8 @@ STATUS = {0: "ok", 1: "bad argument", 2: "CUDA error", 3: "shared-memory budget 
 
 # prologue modes / row maps / epilogues (c3d_common.cuh)
 PRO_NONE, PRO_BN_RELU, PRO_BN_GATE_SWISH, PRO_BNBWD, PRO_ABSDIFF, PRO_MASK_POS = range(6)
-MAP_DENSE, MAP_SUB2, MAP_CONVT_FWD, MAP_CONVT_BWD = range(4)
-EPI_STORE, EPI_RELU_ADD, EPI_SWISH_BWD, EPI_ADD2, EPI_CONVT, EPI_ABSDIFF_BWD = range(6)
+MAP_DENSE, MAP_SUB2 = range(2)
+EPI_STORE, EPI_RELU_ADD, EPI_SWISH_BWD, EPI_ADD2, _EPI_RESERVED4, EPI_ABSDIFF_BWD = range(6)
 
 GEMM_W_CONSTANT = 1     # C3D_GEMM_W_CONSTANT
 
@@ -76,6 +76,7 @@ SIGNATURES = {
     "c3d_change_similarity_fwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _fp, _fp],
     "c3d_change_similarity_bwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _f, _fp, _fp, _fp],
     "c3d_confusion_matrix": [_fp, _i, _fp, _ll, _i, _fp, _fp],
+    "c3d_augment_pairs": [_fp, _i, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp],
 }
 
 LOSS_WS_BYTES = 128      # C3D_LOSS_WS_BYTES

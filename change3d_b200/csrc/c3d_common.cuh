@@ -19,9 +19,9 @@
 // prologue modes for an operand tile (TileSrc.mode)
 enum { PRO_NONE = 0, PRO_BN_RELU = 1, PRO_BN_GATE_SWISH = 2, PRO_BNBWD = 3, PRO_ABSDIFF = 4, PRO_MASK_POS = 5 };
 // row mappings (TileSrc.map)
-enum { MAP_DENSE = 0, MAP_SUB2 = 1, MAP_CONVT_FWD = 2, MAP_CONVT_BWD = 3 };
+enum { MAP_DENSE = 0, MAP_SUB2 = 1 };
 // GEMM epilogues
-enum { EPI_STORE = 0, EPI_RELU_ADD = 1, EPI_SWISH_BWD = 2, EPI_ADD2 = 3, EPI_CONVT = 4, EPI_ABSDIFF_BWD = 5 };
+enum { EPI_STORE = 0, EPI_RELU_ADD = 1, EPI_SWISH_BWD = 2, EPI_ADD2 = 3, EPI_RESERVED4 = 4, EPI_ABSDIFF_BWD = 5 };
 
 // 1 / (1 + e^-v) with the SFU exponential and reciprocal (<= 2 ulp each; inf-safe: e^-v = inf -> 0)
 __device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
@@ -109,11 +109,9 @@ struct TileSrc {
   const float* gate;   // [samples][ld]                                   (PRO_BN_GATE_SWISH, may be null)
   int mode, map;
   int ld;              // row stride (channels incl. pad) of A / A2
-  int K;               // staged width: ld, or 4*ld / 16*ld for the ConvTranspose gathers
+  int K;               // staged width (= ld)
   int OHW, OW;         // GEMM row -> (img, oh, ow)
   int IH, IW;          // source spatial dims
   long long img_stride, img_stride2;  // elements between consecutive images of A / A2
   int frames_per_sample;
-  int cls;             // ConvTranspose parity class (py*2+px) for MAP_CONVT_FWD
-  int seg0;            // first gathered tap staged (gather maps)
 };

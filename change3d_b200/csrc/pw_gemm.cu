@@ -16,10 +16,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const GemmArgs g) {
   constexpr int RI = BM / 16;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSrc a = g.a;
-  const int cls = blockIdx.y / g.nsplit;
-  const int nsp = blockIdx.y - cls * g.nsplit;
-  a.cls = cls;
-  const int n0 = nsp * g.NB;
+  const int n0 = blockIdx.y * g.NB;
   const int NB = g.NB, NBw = NB + 4;
   const int K = a.K, ldS = K + 4;
 
@@ -32,7 +29,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const GemmArgs g) {
 
   // resident weights: Wt[red][out] (zero outside the logical matrix)
   {
-    const float* Wg = g.W + (long long)cls * g.w_cls_stride;
+    const float* Wg = g.W;
     const bool red_fast = (g.w_sr == 1);
     const int total = K * NB;
     for (int idx = tid; idx < total; idx += 256) {
@@ -160,13 +157,6 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const GemmArgs g) {
           float4 a0 = *reinterpret_cast<const float4*>(g.Y + addr), a1 = *reinterpret_cast<const float4*>(g.Y2 + addr);
           st4(g.Y + addr, f4add(a0, t));
           st4(g.Y2 + addr, make_float4(a1.x - t.x, a1.y - t.y, a1.z - t.z, a1.w - t.w));
-        } else {  // EPI_CONVT: GEMM rows index the input grid (j,i); this CTA's parity class picks the output pixel
-          const int py = cls >> 1, px = cls & 1;
-          long long pix = (long long)(2 * m.oh + py) * (2 * OW) + (2 * m.ow + px);
-          long long addr = (long long)m.img * g.out_img_stride + pix * g.Ns + col;
-          v = f4add(v, ldg4(g.bias + col));
-          if (g.E1) v = f4add(v, ldg4(g.E1 + (long long)m.img * g.e1_img_stride + pix * g.Ns + col));
-          st4(g.Y + addr, v);
         }
       }
       if (has_stats && (g.epi == EPI_STORE || (g.epi == EPI_SWISH_BWD && !straddle))) {
@@ -324,13 +314,10 @@ static int num_sms() {
 static void fill_src(TileSrc& t, const c3d_operand& o) {
   t.A = o.A; t.A2 = o.A2; t.bnp = o.bnp; t.coef = o.coef; t.gate = o.gate;
   t.mode = o.mode; t.map = o.map; t.ld = o.ld;
-  const int all_seg = (o.map == MAP_CONVT_FWD) ? 4 : (o.map == MAP_CONVT_BWD) ? 16 : 1;
-  t.seg0 = (all_seg > 1) ? o.seg0 : 0;
-  t.K = ((all_seg > 1 && o.nseg > 0) ? o.nseg : all_seg) * o.ld;
+  t.K = o.ld;
   t.OHW = o.OH * o.OW; t.OW = o.OW; t.IH = o.IH; t.IW = o.IW;
   t.img_stride = o.img_stride; t.img_stride2 = o.img_stride2 ? o.img_stride2 : o.img_stride;
   t.frames_per_sample = o.frames_per_sample > 0 ? o.frames_per_sample : 1;
-  t.cls = 0;
 }
 
 static int check_src(const c3d_operand& o) {
@@ -338,33 +325,28 @@ static int check_src(const c3d_operand& o) {
   if ((o.mode == PRO_BN_RELU || o.mode == PRO_BN_GATE_SWISH || o.mode == PRO_BNBWD) && !o.bnp) return C3D_ERR_ARG;
   if (o.mode == PRO_BNBWD && (!o.A2 || !o.coef)) return C3D_ERR_ARG;
   if ((o.mode == PRO_ABSDIFF || o.mode == PRO_MASK_POS) && !o.A2) return C3D_ERR_ARG;
-  if (o.seg0 < 0 || o.nseg < 0 || (o.map == MAP_CONVT_FWD && o.seg0 + o.nseg > 4) ||
-      (o.map == MAP_CONVT_BWD && o.seg0 + o.nseg > 16))
-    return C3D_ERR_ARG;
-  if (o.mode < 0 || o.mode > PRO_MASK_POS || o.map < 0 || o.map > MAP_CONVT_BWD) return C3D_ERR_ARG;
+  if (o.mode < 0 || o.mode > PRO_MASK_POS || (o.map != MAP_DENSE && o.map != MAP_SUB2)) return C3D_ERR_ARG;
   return C3D_OK;
 }
 
 extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   if (!d || !d->W || !d->Y || d->M <= 0 || d->N <= 0 || d->Ns < d->N || (d->Ns & 3)) return C3D_ERR_ARG;
   if (int e = check_src(d->a)) return e;
-  if (d->epi < 0 || d->epi > EPI_ABSDIFF_BWD) return C3D_ERR_ARG;
+  if (d->epi < 0 || d->epi > EPI_ABSDIFF_BWD || d->epi == EPI_RESERVED4) return C3D_ERR_ARG;
   if (d->epi == EPI_ABSDIFF_BWD && (!d->E1 || !d->E2 || !d->Y2)) return C3D_ERR_ARG;
   if (d->epi == EPI_SWISH_BWD && (!d->E1 || !d->ebnp)) return C3D_ERR_ARG;
-  if (d->epi == EPI_CONVT && !d->bias) return C3D_ERR_ARG;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   GemmArgs g;
   fill_src(g.a, d->a);
-  g.W = d->W; g.w_sr = d->w_sr; g.w_so = d->w_so; g.w_cls_stride = d->w_cls_stride;
+  g.W = d->W; g.w_sr = d->w_sr; g.w_so = d->w_so;
   g.Kred = d->Kred > 0 ? d->Kred : g.a.K;
   g.N = d->N; g.Ns = d->Ns; g.M = d->M; g.Y = d->Y;
   g.out_img_stride = d->out_img_stride ? d->out_img_stride : (long long)g.a.OHW * d->Ns;
   g.epi = d->epi; g.stats = d->stats;
   g.E1 = d->E1; g.e1_img_stride = d->e1_img_stride; g.E2 = d->E2;
-  g.ebnp = d->ebnp; g.egate = d->egate; g.bias = d->bias; g.Y2 = d->Y2;
+  g.ebnp = d->ebnp; g.egate = d->egate; g.Y2 = d->Y2;
   g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : (1LL << 62);
   g.w_const = (d->flags & C3D_GEMM_W_CONSTANT) ? 1 : 0;
-  const int ncls = d->epi == EPI_CONVT ? 4 : 1;
   if (env_flag("C3D_TC", 1)) {
     g.NB = 0; g.nsplit = 1;
     const int r = c3d_launch_pw_gemm_tc(g, num_sms(), stream, env_flag("C3D_TC_LBO", 1) | (env_flag("C3D_TC_HINT", 0) << 1),
@@ -396,10 +378,10 @@ extern "C" int c3d_pw_gemm(const c3d_gemm_desc* d, void* stream_) {
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : per_sm > 3 ? 3 : per_sm;
   long long gx = (long long)num_sms() * per_sm;
-  if (ncls * nsplit > 1) gx = (gx + ncls * nsplit - 1) / (ncls * nsplit);
+  if (nsplit > 1) gx = (gx + nsplit - 1) / nsplit;
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)(ncls * nsplit));
+  dim3 grid((unsigned)gx, (unsigned)nsplit);
   cudaError_t e;
   if (BM == 128) {
     e = cudaFuncSetAttribute(pw_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -6,18 +6,18 @@
 
 struct GemmArgs {
   TileSrc a;
-  const float* W; long long w_sr, w_so, w_cls_stride; int Kred;
+  const float* W; long long w_sr, w_so; int Kred;
   int N, Ns; long long M;
   float* Y; long long out_img_stride;
   int epi;
   double* stats;
   const float* E1; long long e1_img_stride;
   const float* E2;
-  const float* ebnp; const float* egate; const float* bias;
+  const float* ebnp; const float* egate;
   float* Y2;
   long long rows_per_sample;
   int NB;        // columns handled per CTA (multiple of 64)
-  int nsplit;    // grid.y = ncls * nsplit
+  int nsplit;    // grid.y
   int w_const;   // C3D_GEMM_W_CONSTANT: W may be read before pdl_wait()
 };
 
@@ -54,31 +54,8 @@ __device__ __forceinline__ void tile_row_meta(const TileSrc& s, long long row0, 
 // value of the staged tile at (row r, columns kq..kq+3)
 __device__ __forceinline__ float4 tile_fetch(const TileSrc& s, const RowMeta& m, int kq) {
   if (m.img < 0) return f4zero();
-  long long off, off2;
-  int c = kq;
-  if (s.map <= MAP_SUB2) {
-    off = m.off + kq;
-    off2 = m.off2 + kq;
-  } else {
-    int seg = kq / s.ld;
-    c = kq - seg * s.ld;
-    seg += s.seg0;
-    int iy, ix;
-    if (s.map == MAP_CONVT_FWD) {
-      // output pixel (2j+py, 2i+px) gathers input rows {j, j-1} (py=0) or {j+1, j} (py=1); same in x
-      int py = s.cls >> 1, px = s.cls & 1, ty = seg >> 1, tx = seg & 1;
-      iy = m.oh + (py ? (ty ? 0 : 1) : (ty ? -1 : 0));
-      ix = m.ow + (px ? (tx ? 0 : 1) : (tx ? -1 : 0));
-    } else {  // MAP_CONVT_BWD: input pixel (j,i) gathers d_out rows 2j-1+ky, ky=0..3
-      int ky = seg >> 2, kx = seg & 3;
-      iy = 2 * m.oh - 1 + ky;
-      ix = 2 * m.ow - 1 + kx;
-    }
-    if (iy < 0 || iy >= s.IH || ix < 0 || ix >= s.IW) return f4zero();
-    long long pix = (long long)iy * s.IW + ix;
-    off = (long long)m.img * s.img_stride + pix * s.ld + c;
-    off2 = (long long)m.img * s.img_stride2 + pix * s.ld + c;
-  }
+  const int c = kq;
+  const long long off = m.off + kq, off2 = m.off2 + kq;
   float4 v = ldg4(s.A + off);
   switch (s.mode) {
     case PRO_NONE: break;

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
     const float* Wg = g.W;
     const bool k_contig = g.w_sr == 1;
     const bool vec_ok = k_contig && (g.w_so & 3) == 0 && (g.Kred & 3) == 0 && ((reinterpret_cast<uintptr_t>(Wg) & 15) == 0);
-    constexpr int WU = 4;
+    constexpr int WU = 8;
     for (uint32_t base = threadIdx.x; base < total; base += NTHREADS * WU) {
       float4 wv[WU];
       int oo[WU];

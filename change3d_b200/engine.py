@@ -16,9 +16,8 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_CONVT, EPI_RELU_ADD, EPI_STORE, EPI_SWISH_BWD, MAP_CONVT_BWD,
-                   MAP_CONVT_FWD, MAP_DENSE, MAP_SUB2, PRO_ABSDIFF, PRO_BN_GATE_SWISH, PRO_BN_RELU, PRO_BNBWD,
-                   PRO_MASK_POS, PRO_NONE)
+from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_RELU_ADD, EPI_STORE, EPI_SWISH_BWD, MAP_DENSE, MAP_SUB2,
+                   PRO_ABSDIFF, PRO_BN_GATE_SWISH, PRO_BN_RELU, PRO_BNBWD, PRO_MASK_POS, PRO_NONE)
 
 
 import os
@@ -193,25 +192,6 @@ def enhance_forward(x: torch.Tensor, fc_weight: torch.Tensor, P: int, save_mid: 
 # ---------------------------------------------------------------------------------------------
 # ChangeDecoder (model/change_decoder.py:57-81)
 # ---------------------------------------------------------------------------------------------
-_KY = ((1, 3), (0, 2))   # ConvTranspose2d k4 s2 p1: output parity p gathers taps _KY[p] from input rows (j+p, j+p-1)
-
-
-def convt_pack_index(cmid: int, cout: int, device) -> torch.Tensor:
-    """Gather index turning ConvTranspose2d.weight [cmid][cout][4][4] into the four per-parity GEMM
-    matrices packed[cls][(tapy*2+tapx)*cmid + ci][co]."""
-    idx = torch.empty(4, 4 * cmid, cout, dtype=torch.int64)
-    ci = torch.arange(cmid).view(cmid, 1)
-    co = torch.arange(cout).view(1, cout)
-    for py in range(2):
-        for px in range(2):
-            for ty in range(2):
-                for tx in range(2):
-                    ky, kx = _KY[py][ty], _KY[px][tx]
-                    seg = ty * 2 + tx
-                    idx[py * 2 + px, seg * cmid:(seg + 1) * cmid, :] = ((ci * cout + co) * 4 + ky) * 4 + kx
-    return idx.reshape(-1).to(device)
-
-
 def feature_view(f: torch.Tensor):
     """Accepts a (B,C,H,W) feature (typically x[:, :, k] of a channels-last-3d stage output) and returns
     (tensor, img_stride) with NHWC element order inside each image; copies only if the layout is not that."""
@@ -223,7 +203,7 @@ def feature_view(f: torch.Tensor):
     return g, H * W * Cc
 
 
-def decoder_up_forward(up, c_hi, hi_stride: int, h: int, w: int, skip, skip_stride: int, pack_idx: torch.Tensor = None):
+def decoder_up_forward(up, c_hi, hi_stride: int, h: int, w: int, skip, skip_stride: int):
     """One up block: skip + ConvTranspose2d(k4,s2,p1)(Conv2d1x1(c_hi)) -> dense (B,2h,2w,Cout).
     The transposed conv is a dense GEMM t x W_all (all 16 kernel positions per input pixel) + a col2im gather."""
     conv1, convt = up[0], up[1]

@@ -43,16 +43,6 @@ class ChangeDecoder(nn.Module):
                                    nn.ConvTranspose2d(c1, c1, kernel_size=4, stride=2, padding=1))
         num_class = 1 if has_sigmoid else args.num_class
         self.up_c1 = nn.Sequential(nn.Conv2d(c1, num_class, kernel_size=3, stride=1, padding=1, bias=False))
-        self._pack_idx = {}
-
-    def pack_index(self, name: str) -> torch.Tensor:
-        """Cached gather index that re-lays ConvTranspose2d.weight into per-parity GEMM matrices."""
-        convt = getattr(self, name)[1]
-        key = (name, convt.weight.device)
-        if key not in self._pack_idx:
-            self._pack_idx[key] = engine.convt_pack_index(convt.weight.shape[0], convt.weight.shape[1],
-                                                          convt.weight.device)
-        return self._pack_idx[key]
 
     def param_list(self):
         return [self.up_c4[0].weight, self.up_c4[1].weight, self.up_c4[1].bias,

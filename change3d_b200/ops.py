@@ -13,8 +13,8 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_CONVT, EPI_RELU_ADD, EPI_STORE, EPI_SWISH_BWD, MAP_CONVT_BWD,
-                   MAP_CONVT_FWD, MAP_DENSE, MAP_SUB2, PRO_ABSDIFF, PRO_BN_GATE_SWISH, PRO_BN_RELU, PRO_BNBWD,
+from ._lib import (EPI_ABSDIFF_BWD, EPI_ADD2, EPI_RELU_ADD, EPI_STORE, EPI_SWISH_BWD, MAP_DENSE, MAP_SUB2,
+                   PRO_ABSDIFF, PRO_BN_GATE_SWISH, PRO_BN_RELU, PRO_BNBWD,
                    PRO_MASK_POS, PRO_NONE)
 
 BN_EPS = 1e-5
@@ -98,21 +98,19 @@ def operand(A: torch.Tensor, *, ld: int, OH: int, OW: int, IH: Optional[int] = N
 
 def pw_gemm(a: L.Operand, W: torch.Tensor, *, w_sr: int, w_so: int, Kred: int, N: int, Ns: int, M: int,
             Y: torch.Tensor, epi: int = EPI_STORE, stats: Optional[torch.Tensor] = None, out_img_stride: int = 0,
-            w_cls_stride: int = 0, E1=None, e1_img_stride: int = 0, E2=None, ebnp=None, egate=None, bias=None,
-            Y2=None, rows_per_sample: int = 0) -> None:
+            E1=None, e1_img_stride: int = 0, E2=None, ebnp=None, egate=None, Y2=None, rows_per_sample: int = 0) -> None:
     _require_cuda(W, Y)
     d = L.GemmDesc()
     d.a = a
-    d.W = _ptr(W); d.w_sr = w_sr; d.w_so = w_so; d.w_cls_stride = w_cls_stride
+    d.W = _ptr(W); d.w_sr = w_sr; d.w_so = w_so; d.w_cls_stride = 0
     d.Kred = Kred; d.N = N; d.Ns = Ns; d.M = M
     d.Y = _ptr(Y); d.out_img_stride = out_img_stride; d.epi = epi; d.stats = _ptr(stats)
     d.E1 = _ptr(E1); d.e1_img_stride = e1_img_stride; d.E2 = _ptr(E2)
-    d.ebnp = _ptr(ebnp); d.egate = _ptr(egate); d.bias = _ptr(bias); d.Y2 = _ptr(Y2)
+    d.ebnp = _ptr(ebnp); d.egate = _ptr(egate); d.bias = None; d.Y2 = _ptr(Y2)
     d.rows_per_sample = rows_per_sample
     # module parameters are constant within a step; derived weight tensors (re-laid-out copies) are not
     d.flags = L.GEMM_W_CONSTANT if isinstance(W, torch.nn.Parameter) else 0
-    ka = a.ld * (a.nseg if a.nseg else (4 if a.map == MAP_CONVT_FWD else 16 if a.map == MAP_CONVT_BWD else 1))
-    nbytes = 4 * (M * ka * (2 if a.A2 else 1) + M * Ns * (1 + (1 if E1 is not None else 0)) + Kred * N)
+    nbytes = 4 * (M * a.ld * (2 if a.A2 else 1) + M * Ns * (1 + (1 if E1 is not None else 0)) + Kred * N)
     with _Timed("pw_gemm", nbytes, 4 * (M * Kred + M * N + Kred * N)):
         L.check(L.load().c3d_pw_gemm(C.byref(d), _stream()), "c3d_pw_gemm")
 
@@ -121,8 +119,7 @@ def pw_wgrad(p: L.Operand, q: L.Operand, *, M: int, dW: torch.Tensor, dw_sn: int
     _require_cuda(dW)
     d = L.WgradDesc()
     d.p = p; d.q = q; d.M = M; d.dW = _ptr(dW); d.dw_sn = dw_sn; d.dw_sk = dw_sk; d.N = N; d.K = K
-    kq = q.ld * (q.nseg if q.nseg else (16 if q.map == MAP_CONVT_BWD else 1))
-    nbytes = 4 * (M * p.ld * (2 if p.A2 else 1) + M * kq * (2 if q.A2 else 1) + N * K)
+    nbytes = 4 * (M * p.ld * (2 if p.A2 else 1) + M * q.ld * (2 if q.A2 else 1) + N * K)
     with _Timed("pw_wgrad", nbytes, 4 * (M * N + M * K + N * K)):
         L.check(L.load().c3d_pw_wgrad(C.byref(d), _stream()), "c3d_pw_wgrad")
 

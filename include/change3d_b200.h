@@ -35,7 +35,8 @@ int c3d_version(void);
  *   | 4 |A - A2|
  * `map` selects the row addressing:
  *   0 dense (img_stride between images) | 1 stride-2 spatial subsample
- *   | 2 ConvTranspose2d(k4,s2,p1) forward gather (K = 4*ld) | 3 its backward gather (K = 16*ld)
+ *   (2 and 3 were the ConvTranspose2d gather maps of round 1; the transposed convolutions are dense GEMMs +
+ *   c3d_convt_col2im / c3d_convt_im2col now and the maps are rejected)
  * bnp = float[4][ld] (mean, rstd, gamma*rstd, beta) from c3d_bn_finalize; coef = float[2][ld].
  */
 typedef struct c3d_operand {
@@ -51,21 +52,21 @@ typedef struct c3d_operand {
   long long img_stride;       /* elements between images of A */
   long long img_stride2;      /* ... of A2 (0 = same as A) */
   int frames_per_sample;      /* gate row = image / frames_per_sample */
-  int seg0, nseg;             /* gather maps: stage taps [seg0, seg0+nseg) only (nseg 0 = all) */
+  int seg0, nseg;             /* reserved (gather maps of round 1): must be 0 */
 } c3d_operand;
 
-/* Y[M x Ns] = epilogue( prologue(A)[M x K] * Wt[K x N] ),  Wt[red][out] = W[cls*w_cls_stride + red*w_sr + out*w_so]
+/* Y[M x Ns] = epilogue( prologue(A)[M x K] * Wt[K x N] ),  Wt[red][out] = W[red*w_sr + out*w_so]
  * epi: 0 store (+ per-channel sum / sum-of-squares into stats[2][Ns], double, atomically added)
  *      1 Y += relu(acc) in place, previous Y saved to Y2                 (Encoder.enhance, model/trainer.py:88-108)
  *      2 Swish/SE/BN_b backward: du = acc * swish'(gate*bn(E1)); stats[sample][2][Ns] += (du, du*yhat)
  *      3 Y = acc + E1 (+ E2 upsampled x2 at even pixels)                 (residual / shortcut gradient join)
- *      4 ConvTranspose2d scatter: Y[2j+py,2i+px] = acc + bias + E1       (model/change_decoder.py:30-45,71-73)
+ *      4 reserved (ConvTranspose2d scatter of round 1; rejected)
  * Replaces nn.Conv3d 1x1x1 conv_a / conv_c / branch1_conv forward and dgrad (model/x3d.py:173-175,214-216,301-311)
  * and the decoder / enhance 1x1 Conv2d. */
 typedef struct c3d_gemm_desc {
   c3d_operand a;
   const float* W;
-  long long w_sr, w_so, w_cls_stride;
+  long long w_sr, w_so, w_cls_stride;   /* w_cls_stride: reserved, ignored */
   int Kred;                   /* logical reduction length (0 = a's staged width) */
   int N, Ns;                  /* logical / strided output channels */
   long long M;                /* GEMM rows */
@@ -78,7 +79,7 @@ typedef struct c3d_gemm_desc {
   const float* E2;
   const float* ebnp;
   const float* egate;
-  const float* bias;
+  const float* bias;          /* reserved, ignored */
   float* Y2;
   long long rows_per_sample;  /* epi 2: rows per batch sample */
   int flags;                  /* C3D_GEMM_* */
@@ -256,6 +257,18 @@ int c3d_change_similarity_bwd(const float* x1, const float* x2, const long long*
  * 0 <= gt < num_classes (gt float32 when gt_is_float, else int64; pred int64).  num_classes <= 16. */
 int c3d_confusion_matrix(const void* gt, int gt_is_float, const long long* pred, long long n, int num_classes,
                          long long* cm, void* cuda_stream);
+
+/* Input pipeline (data/transforms.py:82-154,166-206 and the SCD / BDA variants :210-612): normalize -> scale ->
+ * random_crop_resize -> random_flip -> random_exchange -> to_tensor of B raw pairs in one launch.
+ * img (B, Hs, Ws, 6) uint8 HWC [pre RGB | post RGB] (or float32, already normalised, when img_is_float);
+ * label (B, Hs, Ws, L) uint8 or NULL; params int[B][8] = {do_crop, x1, y1, flip_rows, flip_cols, exchange_images,
+ * exchange_labels01, 0} (the host draws them in the reference's order).  Outputs: pre / post (B, 3, H, W) float32 NCHW;
+ * label_out (B, L, H, W): float32 ceil(l / 255) when label_mode == 0 (BCD), int64 class ids when 1 (SCD / BDA).
+ * Bilinear / nearest sampling follow cv2.resize (INTER_LINEAR on the normalised float image, INTER_NEAREST on labels).
+ * A crop is only valid when (Hs, Ws) == (H, W) (the reference scales first, then crops the scaled image). */
+int c3d_augment_pairs(const void* img, int img_is_float, const unsigned char* label, const int* params, int B, int Hs,
+                      int Ws, int H, int W, int L, int label_mode, float mean, float std, float* pre, float* post,
+                      void* label_out, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -98,29 +98,27 @@ def test_flat_adam_buffers_on_cpu():
     assert not (opt.flat_p.data_ptr() <= q.data_ptr() < opt.flat_p.data_ptr() + opt.flat_p.numel() * 4)
 
 
-def test_convtranspose_pack_index_reproduces_conv_transpose2d():
-    """The per-parity GEMM matrices built by engine.convt_pack_index, applied the way the kernel gathers
-    (output (2j+py, 2i+px) <- input rows {j, j-1} / {j+1, j}), equal F.conv_transpose2d(k=4, s=2, p=1)."""
-    from change3d_b200.engine import convt_pack_index
+def test_convtranspose_as_dense_gemm_plus_col2im_reproduces_conv_transpose2d():
+    """The decomposition engine.decoder_up_forward uses (U = t x W_all with W_all[ci][(ky,kx,co)] =
+    weight.permute(0, 2, 3, 1), then c3d_convt_col2im: out[y][x] = bias + the <= 4 entries of U with 2j-1+ky = y,
+    2i-1+kx = x) equals F.conv_transpose2d(k=4, s=2, p=1) — host restatement of the index arithmetic."""
     cin, cout, h, w = 5, 3, 4, 6
     g = torch.Generator().manual_seed(0)
     wt = torch.randn(cin, cout, 4, 4, generator=g)
+    bias = torch.randn(cout, generator=g)
     x = torch.randn(1, cin, h, w, generator=g)
-    ref = F.conv_transpose2d(x, wt, None, stride=2, padding=1)
-    packed = wt.reshape(-1)[convt_pack_index(cin, cout, "cpu")].view(4, 4 * cin, cout)
-    xp = F.pad(x, (1, 1, 1, 1))
-    out = torch.zeros(1, cout, 2 * h, 2 * w)
-    for py in range(2):
-        for px in range(2):
-            rows = []
-            for ty in range(2):
-                for tx in range(2):
-                    dy = (0 if ty else 1) if py else (-1 if ty else 0)
-                    dx = (0 if tx else 1) if px else (-1 if tx else 0)
-                    rows.append(xp[0, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w])
-            a = torch.cat(rows, 0).permute(1, 2, 0).reshape(h * w, 4 * cin)
-            out[0, :, py::2, px::2] = (a @ packed[py * 2 + px]).t().reshape(cout, h, w)
-    assert torch.allclose(out, ref, atol=1e-5)
+    ref = F.conv_transpose2d(x, wt, bias, stride=2, padding=1)
+    w_all = wt.permute(0, 2, 3, 1).reshape(cin, 16 * cout)
+    U = (x[0].permute(1, 2, 0).reshape(h * w, cin) @ w_all).view(h, w, 4, 4, cout)
+    out = bias.view(1, 1, cout).repeat(2 * h, 2 * w, 1)
+    for y in range(2 * h):
+        for xx in range(2 * w):
+            for ky in range(4):
+                for kx in range(4):
+                    jn, in_ = y + 1 - ky, xx + 1 - kx
+                    if jn % 2 == 0 and in_ % 2 == 0 and 0 <= jn // 2 < h and 0 <= in_ // 2 < w:
+                        out[y, xx] += U[jn // 2, in_ // 2, ky, kx]
+    assert torch.allclose(out.permute(2, 0, 1).unsqueeze(0), ref, atol=1e-5)
 
 
 def test_convtranspose_as_gemm_col2im_im2col_matches_torch():
