@@ -43,6 +43,15 @@ class WgradDesc(C.Structure):
                 ("dw_sn", C.c_longlong), ("dw_sk", C.c_longlong), ("N", C.c_int), ("K", C.c_int)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("q", _fp), ("k", _fp), ("v", _fp),
+                ("q_ls", C.c_longlong), ("q_bs", C.c_longlong), ("k_ls", C.c_longlong), ("k_bs", C.c_longlong),
+                ("v_ls", C.c_longlong), ("v_bs", C.c_longlong),
+                ("o", _fp), ("o_ls", C.c_longlong), ("o_bs", C.c_longlong), ("P", _fp), ("keep", _fp),
+                ("keep_scale", C.c_float), ("scale", C.c_float),
+                ("B", C.c_int), ("nh", C.c_int), ("hd", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("causal", C.c_int)]
+
+
 _i, _ll, _f = C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes; every function returns int status.  Kept in one table so the CPU test-suite can
@@ -76,6 +85,8 @@ SIGNATURES = {
     "c3d_change_similarity_fwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _fp, _fp],
     "c3d_change_similarity_bwd": [_fp, _fp, _fp, _i, _i, _ll, _ll, _ll, _fp, _f, _fp, _fp, _fp],
     "c3d_confusion_matrix": [_fp, _i, _fp, _ll, _i, _fp, _fp],
+    "c3d_attention_fwd": [C.POINTER(AttnDesc), _fp],
+    "c3d_attention_bwd": [C.POINTER(AttnDesc), _fp, _ll, _ll, _fp, _fp, _fp, _fp],
     "c3d_augment_pairs": [_fp, _i, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _fp, _fp],
 }
 

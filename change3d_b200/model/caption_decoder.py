@@ -1,11 +1,12 @@
 """CaptionDecoder — counterpart of the reference's `model/caption_decoder.py:272-612` (CC task).
 
-Scope note: the captioning head is < 1 % of the FLOPs of a CC step; the
-B200-native part of CC is the encoder feature path (X3D stem..res5 through change3d_b200 kernels,
-`Encoder.forward(..., output_final=True)`).  This head therefore keeps torch's MultiheadAttention /
-LayerNorm / Linear ops, with the reference's module tree so its checkpoints load: every parameter the
-reference registers is registered here under the same name, including the ones its forward never uses
-(self_attn2, multihead_attn, multihead_attn3, linear1/2, norm3, fc_alpha1-3, embedding_1D).
+The module tree is the reference's, so its checkpoints load: every parameter the reference registers is registered
+here under the same name, including the ones its forward never uses (self_attn2, multihead_attn, multihead_attn3,
+linear1/2, norm3, fc_alpha1-3, embedding_1D).  The nn.MultiheadAttention objects are parameter containers: the layer's
+forward runs their scaled-dot-product core (scores, causal mask, softmax, attention dropout, weighted sum, and the
+backward of all of it) on the sm_100a attention kernel (`change3d_b200.attention.fused_mha`, csrc/attention.cu); the
+projections, LayerNorms and the vocabulary projection are library GEMMs / torch ops (< 1 % of
+a CC step's FLOPs).  CUDA tensors only, like the rest of the package.
 
 Two deliberate fixes relative to the reference, neither changing the arithmetic:
   * the decoder layer accepts (and ignores) the `tgt_is_causal` / `memory_is_causal` keywords that
@@ -19,6 +20,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from ..attention import fused_mha
 from .utils import weight_init
 
 
@@ -74,11 +76,13 @@ class Mesh_TransformerDecoderLayer(nn.Module):
     def forward(self, tgt: Tensor, memory: Tensor, tgt_mask: Optional[Tensor] = None,
                 memory_mask: Optional[Tensor] = None, tgt_key_padding_mask: Optional[Tensor] = None,
                 memory_key_padding_mask: Optional[Tensor] = None, **_ignored) -> Tensor:
-        sa = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask,
-                            need_weights=False)[0]
+        if tgt_key_padding_mask is not None or memory_key_padding_mask is not None or memory_mask is not None:
+            raise RuntimeError("Mesh_TransformerDecoderLayer: padding / memory masks are not used by the reference's "
+                               "forward (model/caption_decoder.py:574-612) and are not implemented")
+        # tgt_mask is the causal mask CaptionDecoder.forward builds (model/caption_decoder.py:589-593) or None
+        sa = fused_mha(self.self_attn, tgt, tgt, tgt, causal=tgt_mask is not None)
         x = self.norm1(tgt + self.dropout1(sa))
-        ca, _ = self.multihead_attn2(x, memory, memory, attn_mask=memory_mask,
-                                     key_padding_mask=memory_key_padding_mask, need_weights=True)
+        ca = fused_mha(self.multihead_attn2, x, memory, memory, causal=False)
         return self.norm2(x + self.dropout3(ca))
 
 

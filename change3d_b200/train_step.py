@@ -303,6 +303,7 @@ class CCTrainStep(TrainStep):
                                 params=model.decoder.live_parameters(), grad_clip=grad_clip, autograd_params=True)
         self.cm = None
         self.parts = {}
+        self.outs = ()
         self.use_graph = use_graph
         self.graph = None
         self.static = None
@@ -317,6 +318,7 @@ class CCTrainStep(TrainStep):
         memory = feat.permute(2, 3, 0, 1).reshape(H * W, B, C)                     # 'b c h w -> (h w) b c'
         scores, caps_sorted, decode_lengths, _ = self.model.decoder.forward_device(memory, caps, caplens)
         loss = packed_caption_loss(scores, caps_sorted, decode_lengths)
+        self.outs = (scores.detach(), caps_sorted, decode_lengths)      # what scripts/train_CC.py:148-151 scores
         loss.backward()
         return loss.detach()
 

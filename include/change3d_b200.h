@@ -258,6 +258,31 @@ int c3d_change_similarity_bwd(const float* x1, const float* x2, const long long*
 int c3d_confusion_matrix(const void* gt, int gt_is_float, const long long* pred, long long n, int num_classes,
                          long long* cm, void* cuda_stream);
 
+/* ---- attention core of the captioning head (model/caption_decoder.py:393-423: the scaled-dot-product part of the
+ * nn.MultiheadAttention calls; 8 heads x 24 channels, <= 52 target tokens, 256 memory tokens) and of the cached decode
+ * step of the caption search (scripts/train_CC.py:209-322).  One CTA per (batch, head).
+ * Element (position l, batch b, head h, channel c) of an operand is at ptr + l * ls + b * bs + h * hd + c, so the
+ * (L, B, E) projections and slices of a packed (L, B, 3E) in-projection are addressed in place.
+ *   S = scale * Q K^T;  causal: key j visible to query i iff j <= i + (Lk - Lq);  P = softmax rows;
+ *   dropout: P * keep / (1 - p) with keep (B, nh, Lq, Lk) uint8 (NULL = none);  O = P V.
+ * P (B, nh, Lq, Lk), when not NULL, receives the probabilities before dropout (needed by the backward).
+ * Limits: Lq <= 64, Lk <= 256, hd <= 64. */
+typedef struct c3d_attn_desc {
+  const float* q; const float* k; const float* v;
+  long long q_ls, q_bs, k_ls, k_bs, v_ls, v_bs;
+  float* o;
+  long long o_ls, o_bs;
+  float* P;
+  const unsigned char* keep;
+  float keep_scale;
+  float scale;
+  int B, nh, hd, Lq, Lk, causal;
+} c3d_attn_desc;
+int c3d_attention_fwd(const c3d_attn_desc* d, void* cuda_stream);
+/* dq / dk / dv are written with the strides of q / k / v (dense overwrite of this head's channels). */
+int c3d_attention_bwd(const c3d_attn_desc* d, const float* dO, long long do_ls, long long do_bs, float* dq, float* dk,
+                      float* dv, void* cuda_stream);
+
 /* Input pipeline (data/transforms.py:82-154,166-206 and the SCD / BDA variants :210-612): normalize -> scale ->
  * random_crop_resize -> random_flip -> random_exchange -> to_tensor of B raw pairs in one launch.
  * img (B, Hs, Ws, 6) uint8 HWC [pre RGB | post RGB] (or float32, already normalised, when img_is_float);

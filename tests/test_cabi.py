@@ -45,9 +45,10 @@ def test_ctypes_structs_match_c_layout():
 #include <stddef.h>
 #include "change3d_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(c3d_operand), sizeof(c3d_gemm_desc), sizeof(c3d_wgrad_desc),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(c3d_operand), sizeof(c3d_gemm_desc), sizeof(c3d_wgrad_desc),
          offsetof(c3d_operand, img_stride), offsetof(c3d_operand, seg0), offsetof(c3d_gemm_desc, W),
-         offsetof(c3d_gemm_desc, rows_per_sample), offsetof(c3d_wgrad_desc, dW), offsetof(c3d_gemm_desc, flags));
+         offsetof(c3d_gemm_desc, rows_per_sample), offsetof(c3d_wgrad_desc, dW), offsetof(c3d_gemm_desc, flags),
+         sizeof(c3d_attn_desc), offsetof(c3d_attn_desc, keep_scale), offsetof(c3d_attn_desc, causal));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -57,7 +58,8 @@ int main(void) {
         got = [int(v) for v in subprocess.check_output([exe]).split()]
     want = [C.sizeof(_lib.Operand), C.sizeof(_lib.GemmDesc), C.sizeof(_lib.WgradDesc),
             _lib.Operand.img_stride.offset, _lib.Operand.seg0.offset, _lib.GemmDesc.W.offset,
-            _lib.GemmDesc.rows_per_sample.offset, _lib.WgradDesc.dW.offset, _lib.GemmDesc.flags.offset]
+            _lib.GemmDesc.rows_per_sample.offset, _lib.WgradDesc.dW.offset, _lib.GemmDesc.flags.offset,
+            C.sizeof(_lib.AttnDesc), _lib.AttnDesc.keep_scale.offset, _lib.AttnDesc.causal.offset]
     assert got == want
 
 
@@ -72,6 +74,12 @@ def test_bad_arguments_return_status_without_device(lib):
     assert lib.c3d_dw_conv_fwd(1, 1, 1, 1, None, 1, 7, 8, 8, 24, 24, 1, None) == 1      # T out of range
     assert lib.c3d_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.99, 1e-8, 0.0, 1, 1.0, 0.0, None) == 1
     assert lib.c3d_stem_fwd(None, None, None, None, None, None, None, 1, 3, 8, 8, None) == 1
+    assert lib.c3d_attention_fwd(None, None) == 1
+    ad = _lib.AttnDesc()
+    ad.q = ad.k = ad.v = ad.o = 1
+    ad.B, ad.nh, ad.hd, ad.Lq, ad.Lk = 1, 8, 24, 65, 256          # Lq over the kernel's tile limit
+    assert lib.c3d_attention_fwd(C.byref(ad), None) == 1
+    assert lib.c3d_augment_pairs(None, 0, None, None, 1, 8, 8, 8, 8, 1, 0, 0.5, 0.5, None, None, None, None) == 1
 
 
 def test_product_path_fails_loudly_without_cuda():

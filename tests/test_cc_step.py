@@ -3,8 +3,8 @@
 CPU: the graph-capturable loss `packed_caption_loss` equals the script's pack_padded_sequence + CrossEntropyLoss.
 GPU: `CCTrainStep` — encoder feature path on the sm_100a kernels, captioning head, packed CE, +-grad_clip clamp and the
 two Adam optimizers as fused launches — against the same iteration built from the oracle encoder (fp64 truth, fp32 as
-the noise yardstick), the CaptionDecoder module in fp64 (pinned to the reference's module by tests/test_caption_decoder.py),
-`clip_gradient` and torch.optim.Adam."""
+the noise yardstick), the plain-torch restatement of the captioning head in fp64 (oracle/caption_oracle.py, pinned to the
+reference's module by tests/test_caption_decoder.py), `clip_gradient` and torch.optim.Adam."""
 import argparse
 import contextlib
 import io
@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import caption_oracle as CO
 from oracle import change3d_oracle as O
 from oracle.make_golden_caption import caption_loss
 
@@ -53,27 +54,29 @@ def _decoder(args, dtype, device):
 
 
 def _oracle_iteration(full, dec_sd, args, pre, post, caps, lens, dtype, clip):
-    """The script's iteration on the host: oracle encoder + CaptionDecoder + packed CE, clamp, two Adams."""
+    """The script's iteration on the host: oracle encoder + oracle captioning head + packed CE, clamp, two Adams."""
     s = O.clone_sd(full, dtype=dtype, requires_grad=True)
-    dec = _decoder(args, dtype, "cpu")
-    dec.load_state_dict({k: v.to(dtype) if v.is_floating_point() else v for k, v in dec_sd.items()})
+    dsd = {}
+    for k, v in dec_sd.items():
+        t = v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone()
+        dsd[k] = t.requires_grad_(True) if (v.is_floating_point() and k != "position_encoding.pe") else t
     feat = O.encoder_forward(s, pre.to(dtype), post.to(dtype), 1, True, output_final=True)
     B, C, H, W = feat.shape
     memory = feat.permute(2, 3, 0, 1).reshape(H * W, B, C)
-    scores, caps_sorted, dl, _ = dec(memory, caps, lens)
+    scores, caps_sorted, dl, _ = CO.decoder_forward(dsd, memory, caps, lens, args.n_head)     # dropout 0: train == eval
     loss = caption_loss(scores, caps_sorted, dl)
     loss.backward()
     _oracle_iteration.last = (feat.detach().double(), scores.detach().double())
     enc_params = [v for k, v in s.items() if k.startswith("encoder.") and v.requires_grad and v.grad is not None]
-    dec_params = [p for p in dec.parameters() if p.grad is not None]
+    dec_params = [p for p in dsd.values() if p.requires_grad and p.grad is not None]
     grads = {k: v.grad.clone() for k, v in s.items() if v.requires_grad and v.grad is not None}
-    grads.update({"decoder." + k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None})
+    grads.update({"decoder." + k: p.grad.clone() for k, p in dsd.items() if p.requires_grad and p.grad is not None})
     for ps in (enc_params, dec_params):
         for p in ps:
             p.grad.data.clamp_(-clip, clip)                                   # clip_gradient, model/utils.py:481-491
         torch.optim.Adam(ps, lr=1e-4, weight_decay=1e-5).step()               # scripts/train_CC.py:440-458
     after = {k: v.detach() for k, v in s.items()}
-    after.update({"decoder." + k: p.detach() for k, p in dec.named_parameters()})
+    after.update({"decoder." + k: p.detach() for k, p in dsd.items()})
     return loss.item(), grads, after
 
 
