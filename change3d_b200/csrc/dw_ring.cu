@@ -31,6 +31,27 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// all but the `d` most recent groups have landed (d = rows requested ahead of the computed row, 1..4)
+__device__ __forceinline__ void cp_async_wait_depth(int d) {
+  if (d >= 4) cp_async_wait<4>(); else if (d == 3) cp_async_wait<3>(); else if (d == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+}
+
+// Packed fp32 pairs (fma.rn.f32x2 -> FFMA2: two FMAs per issued instruction).  The depthwise kernels are bound by issue
+// slots, not by the FMA pipe (profiles/r02_summary.md: 62 % issue-active, FFMA 49 % of the instructions), so a thread
+// that owns two ADJACENT CHANNELS gets its inputs as natural 8-byte pairs from the channel-contiguous ring (LDS.64),
+// its weights as pairs of two channels' taps, and halves FFMA, LDS and STG counts alike -- no packing moves.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 struct Geo {
   int N, IH, IW, C, Cs;
@@ -97,7 +118,8 @@ __device__ __forceinline__ Unit decode(long long step, long long s1, const Geo& 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int T>
+// PAIR: thread = (pair of adjacent channels, group of 2 columns) with packed FFMA2 arithmetic; else (channel, 4 columns)
+template <int T, bool PAIR>
 __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
                                                             const float* __restrict__ w, float* __restrict__ Y,
                                                             double* __restrict__ stats, const Geo G) {
@@ -137,16 +159,27 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restr
     }
     if (tid < 2 * CB) s_st[tid] = 0.0;
     pc.set_unit(tid, seg_start, c0, G.IW, G.Cs);
-    float wr[27];
+    // PAIR geometry: channel pair cp2 (channels c0 + 2 cp2, + 1), column group g2 (2 columns)
+    const int cp2 = tid & 15, g2 = tid >> 4;
+    const int cA = c0 + 2 * cp2;
+    float wr[PAIR ? 1 : 27];
+    f2_t wr2[PAIR ? 27 : 1];
+    if (PAIR) {
 #pragma unroll
-    for (int t = 0; t < 27; ++t) wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f;
+      for (int t = 0; t < 27; ++t)
+        wr2[t] = f2_pack((cA < G.C) ? __ldg(w + cA * 27 + t) : 0.f, (cA + 1 < G.C) ? __ldg(w + (cA + 1) * 27 + t) : 0.f);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 27; ++t) wr[t] = (c < G.C) ? __ldg(w + c * 27 + t) : 0.f;
+    }
     // element (sample, frame 0, row 0, strip column -1, block channel 0): only dereferenced where pc.ok says so
     const float* Xu = X + (long long)u.n * T * img + (long long)(seg_start - 1) * G.Cs + c0;
-    float* Yt = Y + (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 4 * grp) * G.Cs + c;   // frame 0, row r0
-    int nvalid = G.IW - (seg_start + 4 * grp);        // valid columns of this thread's group
-    nvalid = nvalid < 0 ? 0 : nvalid > 4 ? 4 : nvalid;
-    if (!c_ok) nvalid = 0;
-    double st_s = 0.0, st_q = 0.0;
+    float* Yt = PAIR ? Y + (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 2 * g2) * G.Cs + cA
+                     : Y + (long long)u.n * T * img + ((long long)u.r0 * G.IW + seg_start + 4 * grp) * G.Cs + c;   // frame 0, row r0
+    int nvalid = G.IW - (seg_start + (PAIR ? 2 * g2 : 4 * grp));        // valid columns of this thread's group
+    nvalid = nvalid < 0 ? 0 : nvalid > (PAIR ? 2 : 4) ? (PAIR ? 2 : 4) : nvalid;
+    if (PAIR ? (cA >= G.Cs) : !c_ok) nvalid = 0;
+    double st_s = 0.0, st_q = 0.0, st_s1 = 0.0, st_q1 = 0.0;      // (PAIR: second channel of the pair)
 
     // ring bookkeeping: slot of row r is (r - r0 + 1) mod R, tracked incrementally
     int issue_row = u.r0 - 1, issue_slot = 0;
@@ -184,18 +217,67 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restr
     // prologue: rows r0-1 .. r0+D requested (slots 0 .. D+1), the first two transformed
     for (int i = 0; i < G.D + 2; ++i) issue();
     __syncthreads();                                  // s_bn is visible
-    if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+    cp_async_wait_depth(G.D);
     transform(u.r0 - 1, 0);
     transform(u.r0, 1);
     int sl = 0;                                       // slot of row oh - 1
     for (int oh = u.r0; oh < u.r1; ++oh) {
       issue();
-      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      cp_async_wait_depth(G.D);
       const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
       const int sl2 = sl1 + 1 >= G.R ? sl1 + 1 - G.R : sl1 + 1;
       transform(oh + 1, sl2);
       __syncthreads();
-      if (nvalid > 0) {
+      if (PAIR && nvalid > 0) {
+        const int toff = (2 * g2) * CB + 2 * cp2;
+        const float* b0 = ring + sl * SF + toff;
+        const float* b1 = ring + sl1 * SF + toff;
+        const float* b2 = ring + sl2 * SF + toff;
+        f2_t acc[T][2];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { acc[t][0] = 0ull; acc[t][1] = 0ull; }
+#pragma unroll
+        for (int ti = 0; ti < T; ++ti) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* rp = (kh == 0 ? b0 : kh == 1 ? b1 : b2) + ti * TS;
+            f2_t in[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) in[j] = *reinterpret_cast<const f2_t*>(rp + j * CB);
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+              const int to = ti - kt + 1;
+              if (to < 0 || to >= T) continue;
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const f2_t wv = wr2[kt * 9 + kh * 3 + kw];
+                acc[to][0] = f2_fma(wv, in[kw], acc[to][0]);
+                acc[to][1] = f2_fma(wv, in[kw + 1], acc[to][1]);
+              }
+            }
+          }
+        }
+        const f2_t ones = f2_pack(1.f, 1.f);
+        f2_t sf2 = 0ull, qf2 = 0ull;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          float* yp = Yt + (long long)t * img;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q < nvalid) {
+              *reinterpret_cast<f2_t*>(yp + q * G.Cs) = acc[t][q];
+              sf2 = f2_fma(acc[t][q], ones, sf2);
+              qf2 = f2_fma(acc[t][q], acc[t][q], qf2);
+            }
+          }
+        }
+        float s_lo, s_hi, q_lo, q_hi;
+        f2_unpack(sf2, s_lo, s_hi);
+        f2_unpack(qf2, q_lo, q_hi);
+        st_s += (double)s_lo; st_s1 += (double)s_hi;
+        st_q += (double)q_lo; st_q1 += (double)q_hi;
+      }
+      if (!PAIR && nvalid > 0) {
         const int toff = (4 * grp) * CB + cl;
         const float* b0 = ring + sl * SF + toff;
         const float* b1 = ring + sl1 * SF + toff;
@@ -247,7 +329,14 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restr
     }
     cp_async_wait<0>();
     if (stats) {      // per-sample statistics of this unit: fold the 8 column groups in shared memory, then one atomic each
-      if (nvalid > 0) { atomicAdd(&s_st[cl], st_s); atomicAdd(&s_st[CB + cl], st_q); }
+      if (nvalid > 0) {
+        if (PAIR) {
+          atomicAdd(&s_st[2 * cp2], st_s); atomicAdd(&s_st[2 * cp2 + 1], st_s1);
+          atomicAdd(&s_st[CB + 2 * cp2], st_q); atomicAdd(&s_st[CB + 2 * cp2 + 1], st_q1);
+        } else {
+          atomicAdd(&s_st[cl], st_s); atomicAdd(&s_st[CB + cl], st_q);
+        }
+      }
       __syncthreads();
       if (tid < 2 * CB) {
         const int k = tid >> 5, cc = tid & 31;
@@ -395,7 +484,7 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
     int sl = 0, sq = 0;                               // slot of row ih - 1; second-ring slot of row ih + 1
     if (FUSED) {
       __syncthreads();                                // s_cb is visible
-      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      cp_async_wait_depth(G.D);
       transform(u.r0 - 1, 0, 0);
       transform(u.r0, 1, 1);
       sq = 2;
@@ -408,7 +497,7 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restr
       for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int q = 0; q < 4; ++q) ya[t][q] = (q < nvalid) ? __ldg(YAt + (long long)t * img + q * G.Cs) : 0.f;
-      if (G.D == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+      cp_async_wait_depth(G.D);
       const int sl1 = sl + 1 >= G.R ? sl + 1 - G.R : sl + 1;
       const int sl2 = sl1 + 1 >= G.R ? sl1 + 1 - G.R : sl1 + 1;
       transform(ih + 1, sl2, sq);
@@ -874,9 +963,15 @@ static bool plan(Geo& G, int T, int N, int IH, int IW, int C, int Cs, size_t ext
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t budget = (size_t)(max_smem + 1024) / ctas_per_sm - 1024;
-  G.D = 2; G.R = 6; G.R2 = second_ring ? G.D + 2 : 0;
-  if ((G.R + G.R2) * slot + extra_smem > budget) { G.D = 1; G.R = 5; G.R2 = second_ring ? G.D + 2 : 0; }
-  if ((G.R + G.R2) * slot + extra_smem > budget) return false;
+  // rows requested ahead of the computed row (C3D_DW_DEPTH, 1..4; default 2: depths 2 / 3 / 4 measured identical at every
+  // stage, profiles/r02_summary.md section 2.4, and the shallower ring leaves shared memory to co-resident kernels)
+  static const int dmax = getenv("C3D_DW_DEPTH") ? atoi(getenv("C3D_DW_DEPTH")) : 2;
+  G.D = dmax < 1 ? 1 : dmax > 4 ? 4 : dmax;
+  for (;; --G.D) {
+    G.R = G.D + 4; G.R2 = second_ring ? G.D + 2 : 0;
+    if ((G.R + G.R2) * slot + extra_smem <= budget) break;
+    if (G.D == 1) return false;
+  }
   smem = (G.R + G.R2) * slot + extra_smem;
   G.total_steps = (long long)N * G.nCB * G.nSEG * IH;
   long long g = (long long)sms * ctas_per_sm;
@@ -897,22 +992,43 @@ int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, flo
   int grid = 0;
   const size_t extra = (size_t)(4 * dwr::CB * 4 + 2 * dwr::CB * 8);        // s_bn [4][CB] floats + s_st [2][CB] doubles
   if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1)) return -1;
+  // channel-pair FFMA2 arithmetic (C3D_DW_PAIR=0: one channel x four columns per thread, scalar FFMA); pairs need an even
+  // channel stride and 8-byte aligned tensors
+  const bool pair = dwr::env_int("C3D_DW_PAIR", 1) && (Cs & 1) == 0 && ((reinterpret_cast<uintptr_t>(Y) & 7) == 0);
   cudaError_t e;
   switch (T) {
     case 3:
-      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      if (pair) {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      } else {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      }
       break;
     case 4:
-      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      if (pair) {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      } else {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      }
       break;
     default:
-      e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return C3D_ERR_SMEM;
-      c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      if (pair) {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      } else {
+        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return C3D_ERR_SMEM;
+        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
+      }
       break;
   }
   return c3d_check_last(cudaGetLastError());

@@ -488,16 +488,27 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_fast_kernel(
     if (n < N) s0 += dps[n * C + cc];
     db2[cc] = s0 + s1;
   }
-  for (int i = tid; i < C * R; i += nthr) {
-    const int cc = i / R, r = i - cc * R;
-    float s0 = 0.f, s1 = 0.f;
-    int n = 0;
-    for (; n + 1 < N; n += 2) {
-      s0 = fmaf(dps[n * C + cc], hid[n * R + r], s0);
-      s1 = fmaf(dps[(n + 1) * C + cc], hid[(n + 1) * R + r], s1);
+  // register tiling: one thread per (channel, 4 consecutive hidden units) -- one dps load and one float4 of the
+  // hidden activations feed four FMAs (the single SM runs out of shared-memory load slots long before FMA slots)
+  if ((R & 3) == 0) {
+    const int R4 = R >> 2;
+    for (int i = tid; i < C * R4; i += nthr) {
+      const int cc = i / R4, r4 = (i - cc * R4) * 4;
+      float4 a = f4zero();
+      for (int n = 0; n < N; ++n) {
+        const float d = dps[n * C + cc];
+        const float4 hv = *reinterpret_cast<const float4*>(hid + n * R + r4);
+        a.x = fmaf(d, hv.x, a.x); a.y = fmaf(d, hv.y, a.y); a.z = fmaf(d, hv.z, a.z); a.w = fmaf(d, hv.w, a.w);
+      }
+      dw2[cc * R + r4] = a.x; dw2[cc * R + r4 + 1] = a.y; dw2[cc * R + r4 + 2] = a.z; dw2[cc * R + r4 + 3] = a.w;
     }
-    if (n < N) s0 = fmaf(dps[n * C + cc], hid[n * R + r], s0);
-    dw2[i] = s0 + s1;
+  } else {
+    for (int i = tid; i < C * R; i += nthr) {
+      const int cc = i / R, r = i - cc * R;
+      float s0 = 0.f;
+      for (int n = 0; n < N; ++n) s0 = fmaf(dps[n * C + cc], hid[n * R + r], s0);
+      dw2[i] = s0;
+    }
   }
   FIN_T(2);
   {
@@ -526,26 +537,58 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_fast_kernel(
     for (int n = 0; n < N; ++n) sres += dpr[n * R + r];
     db1[r] = sres;
   }
-  for (int i = tid; i < R * C; i += nthr) {
-    const int r = i / C, cc = i - r * C;
-    float s0 = 0.f, s1 = 0.f;
-    int n = 0;
-    for (; n + 1 < N; n += 2) {
-      s0 = fmaf(dpr[n * R + r], pin[n * C + cc], s0);
-      s1 = fmaf(dpr[(n + 1) * R + r], pin[(n + 1) * C + cc], s1);
+  if ((R & 3) == 0) {
+    const int R4 = R >> 2;
+    for (int i = tid; i < R4 * C; i += nthr) {
+      const int r4 = (i / C) * 4, cc = i - (i / C) * C;
+      float4 a = f4zero();
+      for (int n = 0; n < N; ++n) {
+        const float pv = pin[n * C + cc];
+        const float4 dv = *reinterpret_cast<const float4*>(dpr + n * R + r4);
+        a.x = fmaf(dv.x, pv, a.x); a.y = fmaf(dv.y, pv, a.y); a.z = fmaf(dv.z, pv, a.z); a.w = fmaf(dv.w, pv, a.w);
+      }
+      dw1[r4 * C + cc] = a.x; dw1[(r4 + 1) * C + cc] = a.y; dw1[(r4 + 2) * C + cc] = a.z; dw1[(r4 + 3) * C + cc] = a.w;
     }
-    if (n < N) s0 = fmaf(dpr[n * R + r], pin[n * C + cc], s0);
-    dw1[i] = s0 + s1;
+  } else {
+    for (int i = tid; i < R * C; i += nthr) {
+      const int r = i / C, cc = i - r * C;
+      float s0 = 0.f;
+      for (int n = 0; n < N; ++n) s0 = fmaf(dpr[n * R + r], pin[n * C + cc], s0);
+      dw1[i] = s0;
+    }
   }
   FIN_T(4);
   if (active) {
+    // dp[k] = sum_r w1[r][c] * dpr[n_k][r]: hidden units outermost, so a weight is loaded once for all of the thread's
+    // samples and the per-sample factors come as float4
+    float dpv[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) dpv[k] = 0.f;
+    if ((R & 3) == 0) {
+      for (int r4 = 0; r4 < R; r4 += 4) {
+        const float w0 = w1s[r4 * C + c], w1v = w1s[(r4 + 1) * C + c], w2v = w1s[(r4 + 2) * C + c], w3 = w1s[(r4 + 3) * C + c];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+          const int n = j + k * G;
+          if (n < N) {
+            const float4 dv = *reinterpret_cast<const float4*>(dpr + n * R + r4);
+            dpv[k] = fmaf(w0, dv.x, fmaf(w1v, dv.y, fmaf(w2v, dv.z, fmaf(w3, dv.w, dpv[k]))));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const int n = j + k * G;
+        if (n < N) for (int r = 0; r < R; ++r) dpv[k] = fmaf(w1s[r * C + c], dpr[n * R + r], dpv[k]);
+      }
+    }
     double S1 = 0.0, S2 = 0.0;
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const int n = j + k * G;
       if (n < N) {
-        float dp = 0.f;
-        for (int r = 0; r < R; ++r) dp = fmaf(w1s[r * C + c], dpr[n * R + r], dp);
+        const float dp = dpv[k];
         S1 += (double)gt[k] * A[k] + (double)dp;
         S2 += (double)gt[k] * Bz[k] + (double)dp * (double)zm[k];
         dpool[(long long)n * Cs + c] = (float)((double)dp / (double)cnt);
@@ -573,6 +616,177 @@ __global__ void __launch_bounds__(1024) se_bn_bwd_fast_kernel(
 #undef FIN_T
 }
 
+// Cluster version of the SE case: the single-CTA kernels above are bound by ONE SM's load bandwidth and shared-memory
+// slots (33-60 us for ~0.5 MFLOP; phase timers in profiles/r02_summary.md).  Eight CTAs of a thread-block cluster split
+// the work: CTA b owns a slice of the channels for everything that is per channel (dps, the fc2 / fc1 weight-gradient
+// columns, dp, the batch sums and BN coefficients) and a slice of the samples for the one reduction over ALL channels
+// (the gradient of the hidden activations).  The two transposes between the slicings go through a small global scratch
+// (dps: N x C floats, dpr: N x R floats) with a cluster barrier after each; scratch reads bypass L1.
+namespace {
+constexpr int SE_CL = 8;          // CTAs per cluster
+constexpr int SE_NT = 256;
+struct SeClArgs {
+  const double* stats; const float* gamma; const float* beta; const float* gate; const float* hidden; const float* zhat_mean;
+  const float* w1; const float* w2;
+  float* scratch;                 // [N * C] dps, then [N * R] dpr
+  float* coef; float* dgamma; float* dbeta; float* dpool; float* dw1; float* db1; float* dw2; float* db2;
+  long long cnt;
+  int N, C, Cs, R, Cb, Nb, H;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+}  // namespace
+
+__global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(SE_NT) se_bn_bwd_cluster_kernel(const SeClArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ double smd[];
+  const int tid = threadIdx.x, rank = blockIdx.x;
+  const int N = a.N, C = a.C, Cs = a.Cs, R = a.R, Cb = a.Cb, Nb = a.Nb;
+  const int c_lo = rank * Cb, c_n = max(0, min(C, c_lo + Cb) - c_lo);
+  const int n_lo = rank * Nb, n_n = max(0, min(N, n_lo + Nb) - n_lo);
+  double* sA = smd;                                   // [N][Cb]
+  double* sB = sA + (size_t)N * Cb;                   // [N][Cb]
+  double* part = sB + (size_t)N * Cb;                 // [Q][2][Cb]   Q = SE_NT / Cb groups of samples
+  const int Q = max(1, min(N, SE_NT / max(Cb, 1)));
+  float* sg = reinterpret_cast<float*>(part + (size_t)Q * 2 * Cb);   // [N][Cb]
+  float* szm = sg + (size_t)N * Cb;
+  float* spin = szm + (size_t)N * Cb;
+  float* sdps = spin + (size_t)N * Cb;
+  float* shid = sdps + (size_t)N * Cb;                // [N][R]
+  float* sdpr = shid + (size_t)N * R;                 // [N][R]
+  float* sw2 = sdpr + (size_t)N * R;                  // [C][R]
+  float* sw1 = sw2 + (size_t)C * R;                   // [R][Cb]
+  float* srow = sw1 + (size_t)R * Cb;                 // [Nb][C]  dps rows of this CTA's samples
+  float* dps_g = a.scratch;
+  float* dpr_g = a.scratch + (size_t)N * C;
+
+  // ---- phase 0: per (sample, own channel): loads, dps, pin ----
+  for (int i = tid; i < N * Cb; i += SE_NT) {
+    const int n = i / Cb, cc = i - n * Cb;
+    double A = 0.0, B = 0.0;
+    float g = 0.f, zm = 0.f, dps = 0.f, pin = 0.f;
+    if (cc < c_n) {
+      const int c = c_lo + cc;
+      A = a.stats[((long long)n * 2) * Cs + c];
+      B = a.stats[((long long)n * 2 + 1) * Cs + c];
+      g = a.gate[(long long)n * Cs + c];
+      zm = a.zhat_mean[(long long)n * Cs + c];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float dg = (float)((double)gam * B + (double)bet * A);      // sum du * z
+      dps = dg * g * (1.f - g);
+      pin = fmaf(zm, gam, bet);
+      dps_g[n * C + c] = dps;
+    }
+    sA[i] = A; sB[i] = B; sg[i] = g; szm[i] = zm; sdps[i] = dps; spin[i] = pin;
+  }
+  for (int i = tid; i < N * R; i += SE_NT) shid[i] = a.hidden[i];
+  for (int i = tid; i < C * R; i += SE_NT) sw2[i] = a.w2[i];
+  for (int i = tid; i < R * Cb; i += SE_NT) {
+    const int r = i / Cb, cc = i - r * Cb;
+    sw1[i] = cc < c_n ? a.w1[r * C + c_lo + cc] : 0.f;
+  }
+  cluster_sync_all();
+
+  // ---- phase 1: gradient of the hidden activations for own samples (all channels); fc2 gradients for own channels ----
+  for (int i = tid; i < n_n * C; i += SE_NT) srow[i] = __ldcg(dps_g + (size_t)n_lo * C + i);
+  __syncthreads();
+  {
+    const int H = a.H, h = tid & (H - 1);
+    for (int base = 0; base < Nb * R; base += SE_NT / H) {            // block-uniform trip count
+      const int o = base + tid / H;
+      const bool ok = o < n_n * R;
+      const int nn = ok ? o / R : 0, r = ok ? o - nn * R : 0;
+      float s0 = 0.f, s1 = 0.f;
+      int c = h;
+      for (; c + H < C; c += 2 * H) {
+        s0 = fmaf(sw2[c * R + r], srow[nn * C + c], s0);
+        s1 = fmaf(sw2[(c + H) * R + r], srow[nn * C + c + H], s1);
+      }
+      if (c < C) s0 = fmaf(sw2[c * R + r], srow[nn * C + c], s0);
+      float sres = s0 + s1;
+      for (int of = H >> 1; of; of >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, of);
+      if (ok && h == 0) {
+        const int n = n_lo + nn;
+        dpr_g[n * R + r] = shid[n * R + r] > 0.f ? sres : 0.f;
+      }
+    }
+  }
+  for (int cc = tid; cc < c_n; cc += SE_NT) {
+    float s0 = 0.f;
+    for (int n = 0; n < N; ++n) s0 += sdps[n * Cb + cc];
+    a.db2[c_lo + cc] = s0;
+  }
+  for (int i = tid; i < c_n * R; i += SE_NT) {
+    const int cc = i / R, r = i - cc * R;
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      s0 = fmaf(sdps[n * Cb + cc], shid[n * R + r], s0);
+      s1 = fmaf(sdps[(n + 1) * Cb + cc], shid[(n + 1) * R + r], s1);
+    }
+    if (n < N) s0 = fmaf(sdps[n * Cb + cc], shid[n * R + r], s0);
+    a.dw2[(c_lo + cc) * R + r] = s0 + s1;
+  }
+  cluster_sync_all();
+
+  // ---- phase 2: fc1 gradients and the batch sums / BN coefficients for own channels ----
+  for (int i = tid; i < N * R; i += SE_NT) sdpr[i] = __ldcg(dpr_g + i);
+  __syncthreads();
+  if (rank == 0)
+    for (int r = tid; r < R; r += SE_NT) {
+      float s0 = 0.f;
+      for (int n = 0; n < N; ++n) s0 += sdpr[n * R + r];
+      a.db1[r] = s0;
+    }
+  for (int i = tid; i < R * c_n; i += SE_NT) {
+    const int r = i / c_n, cc = i - r * c_n;
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) {
+      s0 = fmaf(sdpr[n * R + r], spin[n * Cb + cc], s0);
+      s1 = fmaf(sdpr[(n + 1) * R + r], spin[(n + 1) * Cb + cc], s1);
+    }
+    if (n < N) s0 = fmaf(sdpr[n * R + r], spin[n * Cb + cc], s0);
+    a.dw1[r * C + c_lo + cc] = s0 + s1;
+  }
+  {
+    const int q = tid / max(Cb, 1), cc = tid - q * max(Cb, 1);
+    if (q < Q && cc < c_n) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int n = q; n < N; n += Q) {
+        float dp = 0.f;
+        for (int r = 0; r < R; ++r) dp = fmaf(sw1[r * Cb + cc], sdpr[n * R + r], dp);
+        const int i = n * Cb + cc;
+        S1 += (double)sg[i] * sA[i] + (double)dp;
+        S2 += (double)sg[i] * sB[i] + (double)dp * (double)szm[i];
+        a.dpool[(long long)n * Cs + c_lo + cc] = (float)((double)dp / (double)a.cnt);
+      }
+      part[(q * 2 + 0) * Cb + cc] = S1;
+      part[(q * 2 + 1) * Cb + cc] = S2;
+    }
+  }
+  __syncthreads();
+  const double Mtot = (double)a.cnt * (double)N;
+  for (int cc = tid; cc < c_n; cc += SE_NT) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int q = 0; q < Q; ++q) { S1 += part[(q * 2 + 0) * Cb + cc]; S2 += part[(q * 2 + 1) * Cb + cc]; }
+    const int c = c_lo + cc;
+    a.dgamma[c] = (float)S2;
+    a.dbeta[c] = (float)S1;
+    a.coef[c] = (float)(S1 / Mtot);
+    a.coef[Cs + c] = (float)(S2 / Mtot);
+  }
+  if (rank == SE_CL - 1)                               // pad channels: zero coefficients and pooled gradients
+    for (int c = C + tid; c < Cs; c += SE_NT) {
+      a.coef[c] = 0.f; a.coef[Cs + c] = 0.f;
+      for (int n = 0; n < N; ++n) a.dpool[(long long)n * Cs + c] = 0.f;
+    }
+}
+
 extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long count_per_sample, const float* bnp,
                                       const float* gamma, const float* beta, const float* gate, const float* hidden,
                                       const float* zhat_mean, const float* w1, const float* w2, int C, int Cs, int R,
@@ -591,7 +805,43 @@ extern "C" int c3d_se_bn_bwd_finalize(const double* stats, int N, long long coun
     fprintf(stderr, "[findbg] %s se=%d N=%d C=%d R=%d p0=%lld p1=%lld p2=%lld p3=%lld p4=%lld p5=%lld\n", which, gate != nullptr, N, C, R,
             h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
   };
-  static const bool fast_on = !(getenv("C3D_FIN_FAST") && atoi(getenv("C3D_FIN_FAST")) == 0);
+  // C3D_FIN_FAST: 1 (default) latency-lean single CTA, 2 cluster of 8 CTAs, 0 the round-1 kernel.  The cluster kernel is
+  // the faster one alone (21 vs 39 us) and in a step without the side stream (54.74 vs 55.13 ms), but with the weight
+  // gradients running beside the main stream (the default) an 8-CTA cluster has to wait for eight free SMs of one GPC and
+  // the step gets slower (55.25 vs 54.51 ms, same box): profiles/r02_summary.md section 2.3.
+  static const int fast_mode = getenv("C3D_FIN_FAST") ? atoi(getenv("C3D_FIN_FAST")) : 1;
+  static const bool fast_on = fast_mode != 0;
+  if (gate && fast_mode >= 2 && !dbg_on && C <= 1024 && R <= 64 && N <= 64) {
+    // scratch for the two transposes: one buffer per device, allocated on first use (the first call of a process is
+    // never inside a CUDA-graph capture: train_step warms up eagerly before it captures)
+    static float* scratch[16] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16) {
+      if (!scratch[dev] && cudaMalloc(&scratch[dev], (size_t)(64 * 1024 + 64 * 64) * sizeof(float)) != cudaSuccess) scratch[dev] = nullptr;
+      if (scratch[dev]) {
+        SeClArgs a;
+        a.stats = stats; a.gamma = gamma; a.beta = beta; a.gate = gate; a.hidden = hidden; a.zhat_mean = zhat_mean;
+        a.w1 = w1; a.w2 = w2; a.scratch = scratch[dev];
+        a.coef = coef; a.dgamma = dgamma; a.dbeta = dbeta; a.dpool = dpool; a.dw1 = dw1; a.db1 = db1; a.dw2 = dw2; a.db2 = db2;
+        a.cnt = count_per_sample; a.N = N; a.C = C; a.Cs = Cs; a.R = R;
+        a.Cb = (C + SE_CL - 1) / SE_CL; a.Nb = (N + SE_CL - 1) / SE_CL;
+        int H = 1;
+        while (2 * H * a.Nb * R <= SE_NT && 2 * H <= 32) H *= 2;
+        a.H = H;
+        int Q = SE_NT / a.Cb;
+        if (Q > N) Q = N;
+        if (Q < 1) Q = 1;
+        const size_t csmem = ((size_t)2 * N * a.Cb + (size_t)Q * 2 * a.Cb) * sizeof(double) +
+                             ((size_t)4 * N * a.Cb + (size_t)2 * N * R + (size_t)C * R + (size_t)R * a.Cb + (size_t)a.Nb * C) * sizeof(float);
+        if (a.Cb <= SE_NT && csmem <= 200 * 1024 &&
+            cudaFuncSetAttribute(se_bn_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem) == cudaSuccess) {
+          se_bn_bwd_cluster_kernel<<<SE_CL, SE_NT, csmem, (cudaStream_t)stream_>>>(a);
+          return c3d_check_last(cudaGetLastError());
+        }
+      }
+    }
+  }
   if (gate && fast_on && C <= 1024 && R <= 64) {
     int G = 1024 / C;
     if (G > N) G = N;

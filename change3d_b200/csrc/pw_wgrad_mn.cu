@@ -43,6 +43,8 @@ struct Params {
   int pf_dist;             // L2 prefetch distance in stages (0 = off), counted from the stage being loaded
   int ncat;                // 1: [S hi | S lo] is read as ONE operand of 2 * NsP columns (Bh x [Sh | Sl] in one MMA)
   int stack;               // 1 (needs ncat, 2 * Gb <= 4): [B hi ; B lo] fills the 128 lanes, one MMA per k-step
+  int nacc;                // accumulator sets used round-robin over the k-steps (power of two; tuning option, default 1),
+                           // summed by the final epilogue
   uint32_t stage_bytes, off_blo, off_shi, off_slo, grp_bytes;
   unsigned long long* dbg;
 };
@@ -362,7 +364,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       const uint64_t tmpl = make_desc_mn128(0, lbo, sbo);      // start address (16-byte units, bits 0-13) is added per use
       const uint32_t blk16 = (4u * P.grp_bytes) >> 4;           // descriptor units between 128-channel blocks
       const int ksteps = P.PT / 8;
-      uint32_t first = 0;
+      const uint32_t set_cols = (uint32_t)(P.nblocks * 2 * P.NsP);
+      uint32_t kcount = 0;                                       // k-steps issued so far: set = kcount % nacc
       int stage = 0;
       uint32_t phase = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
@@ -372,9 +375,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         const uint32_t st = base_u32 + (uint32_t)stage * P.stage_bytes;
         uint64_t dsh = tmpl + (uint64_t)((st + P.off_shi) >> 4), dsl = tmpl + (uint64_t)((st + P.off_slo) >> 4);
         uint64_t dbh = tmpl + (uint64_t)(st >> 4), dbl = tmpl + (uint64_t)((st + P.off_blo) >> 4);
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int ks = 0; ks < ksteps; ++ks, ++kcount) {
+          const uint32_t set = kcount & (uint32_t)(P.nacc - 1);
+          const uint32_t first = kcount >= (uint32_t)P.nacc ? 1u : 0u;      // a set's first MMA overwrites
           for (int b = 0; b < P.nblocks; ++b) {
-            const uint32_t db = tmem_base + (uint32_t)(b * 2 * P.NsP);
+            const uint32_t db = tmem_base + set * set_cols + (uint32_t)(b * 2 * P.NsP);
             const uint64_t bo = (uint64_t)((uint32_t)b * blk16);
             if (ncat) {
               umma_tf32_if(leader, db, dbh + bo, dsh, idesc2, first);
@@ -385,7 +390,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
               umma_tf32_if(leader, db + (uint32_t)P.NsP, dbh + bo, dsl, idesc, 1u);
             }
           }
-          first = 1u;
           dsh += 64; dsl += 64; dbh += 64; dbl += 64;           // next 8 pixels: two 512-byte atoms
         }
         umma_commit_if(leader, smem_u32(empty + stage));
@@ -404,6 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
       tc_fence_after();
       float* S = reinterpret_cast<float*>(base) + warp * (32 * 33);
       const bool transpose = P.dw_ss == 1 && P.dw_sb != 1;
+      const long long total_ks = (long long)my_tiles * (P.PT / 8);
+      const int sets_used = total_ks < P.nacc ? (int)total_ks : P.nacc;      // sets that received at least one MMA
       for (int b = 0; b < P.nblocks; ++b) {
         // stacked operand: lanes 32 * Gb .. 64 * Gb hold the B-lo rows of channels 0 .. 32 * Gb (their products with
         // [Sh | Sl] are added to the same dW entries by the atomics below); lanes past 64 * Gb hold nothing
@@ -412,20 +418,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         const int bc = bc0 + lane;
         const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 2 * P.NsP);
         for (int c0 = 0; c0 < P.NsP; c0 += 32) {
-          float r[32], r2[32];
-          tmem_ld32(t_main + (uint32_t)c0, r);
-          tmem_ld32(t_main + (uint32_t)(P.NsP + c0), r2);
+          float r[32];
+          {
+            float r2[32];
+            tmem_ld32(t_main + (uint32_t)c0, r);
+            tmem_ld32(t_main + (uint32_t)(P.NsP + c0), r2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] += r2[j];
+          }
+          for (int sidx = 1; sidx < sets_used; ++sidx) {        // further round-robin accumulator sets
+            const uint32_t so = (uint32_t)(sidx * P.nblocks * 2 * P.NsP);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              float q[32];
+              tmem_ld32(t_main + so + (uint32_t)(half * P.NsP + c0), q);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] += q[j];
+            }
+          }
           if (!transpose) {
             if (bc < P.Nb) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int sc = c0 + j;
-                if (sc < P.Ns_) atomicAdd(P.dW + (long long)bc * P.dw_sb + (long long)sc * P.dw_ss, r[j] + r2[j]);
+                if (sc < P.Ns_) atomicAdd(P.dW + (long long)bc * P.dw_sb + (long long)sc * P.dw_ss, r[j]);
               }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) S[lane * 33 + j] = r[j] + r2[j];
+            for (int j = 0; j < 32; ++j) S[lane * 33 + j] = r[j];
             __syncwarp();
             const int sc = c0 + lane;
             if (sc < P.Ns_) {
@@ -508,9 +529,16 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
     P.ncat = (cat_env >= 1 && 2 * P.NsP <= 256) ? 1 : 0;
     P.stack = (cat_env >= 2 && P.ncat && 2 * P.Gb <= 4) ? 1 : 0;
   }
+  if (P.nblocks * 2 * P.NsP > 512) return -1;
+  {      // C3D_WMN_NACC: round-robin accumulator sets (default 1: 1 / 2 / 4 sets measured identical at every stage,
+         // profiles/r02_summary.md -- the MMA chain is not what bounds this kernel; kept as a tuning option)
+    static const int nacc_env = getenv("C3D_WMN_NACC") ? atoi(getenv("C3D_WMN_NACC")) : 1;
+    int nacc = 1;
+    while (2 * nacc <= nacc_env && 2 * nacc * P.nblocks * 2 * P.NsP <= 512) nacc *= 2;
+    P.nacc = nacc;
+  }
   int cols = 32;
-  while (cols < P.nblocks * 2 * P.NsP) cols <<= 1;
-  if (cols > 512) return -1;
+  while (cols < P.nacc * P.nblocks * 2 * P.NsP) cols <<= 1;
   P.tmem_cols = cols;
   P.swap_lbo = swap_lbo;
   P.dbg = nullptr;

@@ -50,13 +50,15 @@ class _Timed:
 
 
 def pad8(c: int) -> int:
-    """Channel stride of the bottleneck's inner tensors: a multiple of 8 (54->56, 108->112, 432), and of 16 floats
-    (64 bytes, the DRAM access granularity) where that costs under 5 % (216->224): with a 864-byte pixel stride every
-    second pixel's 128-byte channel block starts mid-atom and the depthwise kernels, which read one channel block
-    per CTA, fetch 1.25x their bytes from HBM (profiles/r02_summary.md).  C3D_PAD16=0 keeps the multiple of 8."""
+    """Channel stride of the bottleneck's inner tensors: a multiple of 8, and of 16 floats (64 bytes, the DRAM access
+    granularity) where that costs at most C3D_PAD16_PCT per cent (default 20: 54 -> 64, 216 -> 224; 108 -> 112 and 432
+    already are).  With a pixel stride that is not a multiple of 64 bytes the depthwise kernels, which read one
+    32-channel block per CTA, straddle DRAM atoms: measured 1.9-2.0x their input bytes from HBM at 56 / 216 channels
+    against 1.08x at 64 (profiles/r02_summary.md).  C3D_PAD16=0 keeps the multiple of 8."""
     c8 = (c + 7) // 8 * 8
     c16 = (c + 15) // 16 * 16
-    if c16 != c8 and (c16 - c) * 20 <= c and os.environ.get("C3D_PAD16", "1") == "1":
+    pct = int(os.environ.get("C3D_PAD16_PCT", "20"))
+    if c16 != c8 and (c16 - c) * 100 <= pct * c and os.environ.get("C3D_PAD16", "1") == "1":
         return c16
     return c8
 

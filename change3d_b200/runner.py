@@ -158,6 +158,13 @@ def train(args, train_loader, step: BCDTrainStep, epoch: int, max_batches: int, 
             res_time = (max_batches * args.max_epochs - iter_idx - cur_iter) * (time.time() - t_epoch) / done / 3600
             print(f"[epoch {epoch}] [iter {done}/{len(train_loader)} {res_time:.2f}h] "
                   f"[lr {step.opt.param_groups[0]['lr']:.6f}] [bn_loss {loss.item():.4f}] ")
+    # data parallel: every rank saw 1/world of the epoch -- reduce the loss sum, the step count and the training confusion
+    # matrix so that rank 0 logs / checkpoints whole-epoch numbers (the reference is single-process)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        tot = torch.stack([loss_sum.double(), torch.tensor(float(n), dtype=torch.float64, device=dev)])
+        dist.all_reduce(tot)
+        dist.all_reduce(step.cm)
+        return float(tot[0].item()) / max(1.0, float(tot[1].item())), step.scores(), lr
     return float(loss_sum.item()) / max(1, n), step.scores(), lr
 
 
@@ -191,6 +198,10 @@ def setup_logger(args, save_path: str):
 
 def _state_dict_copy(model) -> dict:
     # parameters are views of the flat Adam buffer: save independent tensors, reference key schema
+    # (BatchNorm running statistics are this rank's: per-rank statistics are the reference's semantics for plain
+    # nn.BatchNorm3d, and rank 0's buffers are what DDP's broadcast_buffers would keep.)  The 'optimizer' entry of a
+    # checkpoint is FlatAdam.state_dict() -- flat exp_avg / exp_avg_sq buffers in parameter order and one step count, not
+    # torch.optim.Adam's per-parameter dict; the reference's --resume never restores it (model/utils.py:205-232).
     return {k: v.detach().clone() for k, v in model.state_dict().items()}
 
 

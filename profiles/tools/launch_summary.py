@@ -15,7 +15,7 @@ FAMILIES = [
     (r"bn_add_relu", "bn_add_relu"), (r"stem_bwd", "stem_bwd"), (r"stem_fwd", "stem_fwd"),
     (r"convt_col2im", "convt_col2im"), (r"convt_im2col", "convt_im2col"), (r"dec_head_fwd", "dec_head_fwd"),
     (r"dec_head_bwd", "dec_head_bwd"), (r"bce_dice_fwd|ce2d_fwd|sim_kernel<\d+, false|sim_kernel<\(int\)\d+, \(bool\)0", "loss_fwd"),
-    (r"bce_dice_bwd|ce2d_bwd|sim_kernel", "loss_bwd"), (r"finalize", "finalizers"), (r"adam_kernel", "adam"),
+    (r"bce_dice_bwd|ce2d_bwd|sim_kernel", "loss_bwd"), (r"finalize|se_bn_bwd_fast|se_bn_bwd_cluster", "finalizers"), (r"adam_kernel", "adam"),
 ]
 
 
