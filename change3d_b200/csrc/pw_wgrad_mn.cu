@@ -46,6 +46,11 @@ struct Params {
   int nacc;                // accumulator sets used round-robin over the k-steps (power of two; tuning option, default 1),
                            // summed by the final epilogue
   uint32_t stage_bytes, off_blo, off_shi, off_slo, grp_bytes;
+  // raw landing ring (TMA destinations), decoupled from the operand ring the MMAs read: a landing slot is re-requested as
+  // soon as the producers have READ it, so the loads run ahead of the transform instead of behind the MMAs
+  // (profiles/r02_summary.md section 2.2: with in-place stages ~1 stage per SM was in flight).  nraw == 0: in place.
+  int nraw;
+  uint32_t raw_bytes, raw_b2, raw_s, raw_s2;      // slot size; offsets of B's second tensor, S, S's second tensor
   unsigned long long* dbg;
 };
 
@@ -69,7 +74,7 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo
 // inside one batch sample -- no per-row selects.
 template <int MODE, bool FULL>
 __device__ __forceinline__ void transform_rows(const ChanParams& cp, float4 g0, float4 g1, int gsplit, int nvalid, bool kvalid,
-                                               float* hi, float* lo, int lane, int q0) {
+                                               const float* src, const float* src2, float* hi, float* lo, int lane, int q0) {
   constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
   const int u = lane & 7, rsub = lane >> 3;
   int o[4];
@@ -89,8 +94,8 @@ __device__ __forceinline__ void transform_rows(const ChanParams& cp, float4 g0, 
   float4 v[4], v2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(hi + o[i]);
-    v2[i] = HAS2 ? *reinterpret_cast<const float4*>(lo + o[i]) : f4zero();
+    v[i] = *reinterpret_cast<const float4*>(src + o[i]);
+    v2[i] = HAS2 ? *reinterpret_cast<const float4*>(src2 + o[i]) : f4zero();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -113,7 +118,8 @@ __device__ __forceinline__ void transform_rows(const ChanParams& cp, float4 g0, 
 // at physical unit (((u >> 1) ^ (r & 3)) << 1) | (u & 1).  A lane keeps its logical unit (4 channels) for all rows; one instruction covers four
 // consecutive rows = 512 contiguous bytes, each lane its own 16 bytes (conflict-free).
 template <int MODE>
-__device__ __forceinline__ void transform_group(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
+__device__ __forceinline__ void transform_group(const TileSrc& s, long long M, long long row0, int PT, int g, const float* src,
+                                                const float* src2, float* hi, float* lo,
                                                 int lane, int q0) {      // q0: first 4-row quad of this job's 16 rows
   constexpr bool HAS2 = (MODE == PRO_BNBWD || MODE == PRO_ABSDIFF || MODE == PRO_MASK_POS);
   const int u = lane & 7, rsub = lane >> 3;
@@ -144,8 +150,8 @@ __device__ __forceinline__ void transform_group(const TileSrc& s, long long M, l
     for (int i = 0; i < 4; ++i) {
       const int r = 4 * (i0 + i) + rsub;
       const int o = r * 32 + (((((u >> 1) ^ (r & 3)) << 1) | (u & 1)) << 2);
-      v[i] = (i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(hi + o) : f4zero();
-      v2[i] = (HAS2 && i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(lo + o) : f4zero();
+      v[i] = (i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(src + o) : f4zero();
+      v2[i] = (HAS2 && i0 + i < PT / 4) ? *reinterpret_cast<const float4*>(src2 + o) : f4zero();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -165,15 +171,15 @@ __device__ __forceinline__ void transform_group(const TileSrc& s, long long M, l
   }
 }
 
-__device__ __forceinline__ void transform_group_any(const TileSrc& s, long long M, long long row0, int PT, int g, float* hi, float* lo,
-                                                    int lane, int q0) {
+__device__ __forceinline__ void transform_group_any(const TileSrc& s, long long M, long long row0, int PT, int g, const float* src,
+                                                    const float* src2, float* hi, float* lo, int lane, int q0) {
   switch (s.mode) {
-    case PRO_NONE: transform_group<PRO_NONE>(s, M, row0, PT, g, hi, lo, lane, q0); break;
-    case PRO_BN_RELU: transform_group<PRO_BN_RELU>(s, M, row0, PT, g, hi, lo, lane, q0); break;
-    case PRO_BN_GATE_SWISH: transform_group<PRO_BN_GATE_SWISH>(s, M, row0, PT, g, hi, lo, lane, q0); break;
-    case PRO_BNBWD: transform_group<PRO_BNBWD>(s, M, row0, PT, g, hi, lo, lane, q0); break;
-    case PRO_ABSDIFF: transform_group<PRO_ABSDIFF>(s, M, row0, PT, g, hi, lo, lane, q0); break;
-    default: transform_group<PRO_MASK_POS>(s, M, row0, PT, g, hi, lo, lane, q0); break;
+    case PRO_NONE: transform_group<PRO_NONE>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
+    case PRO_BN_RELU: transform_group<PRO_BN_RELU>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
+    case PRO_BN_GATE_SWISH: transform_group<PRO_BN_GATE_SWISH>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
+    case PRO_BNBWD: transform_group<PRO_BNBWD>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
+    case PRO_ABSDIFF: transform_group<PRO_ABSDIFF>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
+    default: transform_group<PRO_MASK_POS>(s, M, row0, PT, g, src, src2, hi, lo, lane, q0); break;
   }
 }
 
@@ -188,17 +194,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
 #define DBG_T(acc, stmt) do { if (dbg_on) { const long long t_ = clock64(); stmt; acc += clock64() - t_; } else { stmt; } } while (0)
   // 1024-byte alignment of the stages (swizzle atoms): the dynamic shared window may start at any 16-byte boundary
   unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)P.nstage * P.stage_bytes);
-  uint64_t* rawfull = bars;                  // [nstage] TMA bytes have landed
+  // operand ring [nstage], then (decoupled mode) the raw landing ring [nraw]
+  unsigned char* rawbase = base + (size_t)P.nstage * P.stage_bytes;
+  const int nslots = P.nraw > 0 ? P.nraw : P.nstage;       // landing slots (in-place mode: the stages themselves)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rawbase + (size_t)P.nraw * P.raw_bytes);
+  uint64_t* rawfull = bars;                  // [nslots] TMA bytes have landed
   uint64_t* full = bars + MAX_STAGES;        // [nstage] NPW producer warps have transformed the stage
   uint64_t* empty = full + MAX_STAGES;       // [nstage] the MMAs reading the stage have retired
-  uint64_t* done = empty + MAX_STAGES;       // [1]
+  uint64_t* rawempty = empty + MAX_STAGES;   // [nraw]   NPW producer warps have read the landing slot
+  uint64_t* done = rawempty + MAX_STAGES;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.nstage; ++i) {
-      mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(full + i), NPW); mbar_init(smem_u32(empty + i), 1);
-    }
+    for (int i = 0; i < P.nstage; ++i) { mbar_init(smem_u32(full + i), NPW); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(rawempty + i), NPW); }
     mbar_init(smem_u32(done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -237,6 +246,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
     const int g_0 = big0 ? grp0 : grp0 - P.Gb;
     const uint32_t hi_off0 = big0 ? (uint32_t)g_0 * (P.grp_bytes >> 2) : (P.off_shi >> 2) + (uint32_t)g_0 * (P.grp_bytes >> 2);
     const uint32_t lo_rel0 = big0 ? (P.off_blo >> 2) : ((P.off_slo - P.off_shi) >> 2);
+    // landing-slot offsets (floats) of this job's tensors
+    const uint32_t src_off0 = (big0 ? 0u : (P.raw_s >> 2)) + (uint32_t)g_0 * (P.grp_bytes >> 2);
+    const uint32_t src2_off0 = (big0 ? (P.raw_b2 >> 2) : (P.raw_s2 >> 2)) + (uint32_t)g_0 * (P.grp_bytes >> 2);
+    const bool decoupled = P.nraw > 0;
     int k0 = g_0 * 32 + 4 * (lane & 7);
     const bool kvalid0 = k0 < s0.K;
     if (!kvalid0) k0 = 0;
@@ -255,14 +268,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         samp_end = (samp + 1) * rps0;
         g0 = ldg4(s0.gate + (long long)samp * s0.ld + k0);
       }
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, rslot = 0;
+      uint32_t phase = 0, rphase = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
-        DBG_T(d_a, mbar_wait(smem_u32(rawfull + stage), phase));
+        DBG_T(d_a, mbar_wait(smem_u32(rawfull + rslot), rphase));
+        if (decoupled) DBG_T(d_b, mbar_wait(smem_u32(empty + stage), phase ^ 1u));      // operand slot drained by its MMAs
         ++d_n;
         const long long t_x = dbg_on ? clock64() : 0;
         const long long row0 = (t_begin + ti) * P.PT;
         float* st = reinterpret_cast<float*>(base + (size_t)stage * P.stage_bytes);
+        const float* rw = decoupled ? reinterpret_cast<const float*>(rawbase + (size_t)rslot * P.raw_bytes) : nullptr;
         if (hoist0) {
           int gsplit = P.PT;
           if (gated0) {
@@ -275,25 +290,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
           const long long left = P.M - row0;
           const int nvalid = left < P.PT ? (int)left : P.PT;
           float* hi = st + hi_off0;
-          if (nvalid == P.PT && gsplit >= P.PT) transform_rows<MODE, true>(cp, g0, g1, gsplit, nvalid, kvalid0, hi, hi + lo_rel0, lane, q00);
-          else transform_rows<MODE, false>(cp, g0, g1, gsplit, nvalid, kvalid0, hi, hi + lo_rel0, lane, q00);
+          const float* src = decoupled ? rw + src_off0 : hi;
+          const float* src2 = decoupled ? rw + src2_off0 : hi + lo_rel0;
+          if (nvalid == P.PT && gsplit >= P.PT) transform_rows<MODE, true>(cp, g0, g1, gsplit, nvalid, kvalid0, src, src2, hi, hi + lo_rel0, lane, q00);
+          else transform_rows<MODE, false>(cp, g0, g1, gsplit, nvalid, kvalid0, src, src2, hi, hi + lo_rel0, lane, q00);
         }
         for (int job = hoist0 ? pw + NPW : pw; job < njobs; job += NPW) {
           const int grp = job / nrc, q0 = (job - grp * nrc) * 4;      // (operand, channel group), 16-row chunk
           if (grp < P.Gb) {
             float* hi = st + (size_t)grp * (P.grp_bytes >> 2);
-            transform_group_any(P.big, P.M, row0, P.PT, grp, hi, hi + (P.off_blo >> 2), lane, q0);
+            float* lo = hi + (P.off_blo >> 2);
+            const float* src = decoupled ? rw + (size_t)grp * (P.grp_bytes >> 2) : hi;
+            const float* src2 = decoupled ? rw + (P.raw_b2 >> 2) + (size_t)grp * (P.grp_bytes >> 2) : lo;
+            transform_group_any(P.big, P.M, row0, P.PT, grp, src, src2, hi, lo, lane, q0);
           } else {
             const int g = grp - P.Gb;
             float* hi = st + (P.off_shi >> 2) + (size_t)g * (P.grp_bytes >> 2);
-            transform_group_any(P.small, P.M, row0, P.PT, g, hi, hi + ((P.off_slo - P.off_shi) >> 2), lane, q0);
+            float* lo = hi + ((P.off_slo - P.off_shi) >> 2);
+            const float* src = decoupled ? rw + (P.raw_s >> 2) + (size_t)g * (P.grp_bytes >> 2) : hi;
+            const float* src2 = decoupled ? rw + (P.raw_s2 >> 2) + (size_t)g * (P.grp_bytes >> 2) : lo;
+            transform_group_any(P.small, P.M, row0, P.PT, g, src, src2, hi, lo, lane, q0);
           }
         }
         if (dbg_on) d_c += clock64() - t_x;
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(full + stage));
+        if (lane == 0) {
+          mbar_arrive(smem_u32(full + stage));
+          if (decoupled) mbar_arrive(smem_u32(rawempty + rslot));       // this warp has read its part of the landing slot
+        }
         if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+        if (decoupled) { if (++rslot == P.nraw) { rslot = 0; rphase ^= 1u; } }
+        else { rslot = stage; rphase = phase; }
       }
     };
     switch (s0.mode) {
@@ -310,23 +338,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
     const uint32_t bytes = (uint32_t)P.PT * 128u * (uint32_t)(P.Gb * (big2 ? 2 : 1) + P.Gs * (small2 ? 2 : 1));
     int stage = 0;
     uint32_t phase = 0;
+    const bool decoupled = P.nraw > 0;
+    const int nslots_ = decoupled ? P.nraw : P.nstage;
+    const uint32_t rawbase_u32 = base_u32 + (uint32_t)P.nstage * P.stage_bytes;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      DBG_T(d_a, mbar_wait(smem_u32(empty + stage), phase ^ 1u));
+      // in place: the stage's MMAs have retired; decoupled: the producers have read the landing slot
+      DBG_T(d_a, mbar_wait(smem_u32((decoupled ? rawempty : empty) + stage), phase ^ 1u));
       if (lane == 0) {
         const int r0 = (int)((t_begin + ti) * P.PT);
-        const uint32_t st = base_u32 + (uint32_t)stage * P.stage_bytes;
+        const uint32_t st = decoupled ? rawbase_u32 + (uint32_t)stage * P.raw_bytes : base_u32 + (uint32_t)stage * P.stage_bytes;
+        const uint32_t o_b2 = decoupled ? P.raw_b2 : P.off_blo, o_s = decoupled ? P.raw_s : P.off_shi, o_s2 = decoupled ? P.raw_s2 : P.off_slo;
         const uint32_t bar = smem_u32(rawfull + stage);
         mbar_expect_tx(bar, bytes);
         for (int g = 0; g < P.Gb; ++g) {
           tma_load_2d(st + (uint32_t)g * P.grp_bytes, &tmB, g * 32, r0, bar);
-          if (big2) tma_load_2d(st + P.off_blo + (uint32_t)g * P.grp_bytes, &tmB2, g * 32, r0, bar);
+          if (big2) tma_load_2d(st + o_b2 + (uint32_t)g * P.grp_bytes, &tmB2, g * 32, r0, bar);
         }
         for (int g = 0; g < P.Gs; ++g) {
-          tma_load_2d(st + P.off_shi + (uint32_t)g * P.grp_bytes, &tmS, g * 32, r0, bar);
-          if (small2) tma_load_2d(st + P.off_slo + (uint32_t)g * P.grp_bytes, &tmS2, g * 32, r0, bar);
+          tma_load_2d(st + o_s + (uint32_t)g * P.grp_bytes, &tmS, g * 32, r0, bar);
+          if (small2) tma_load_2d(st + o_s2 + (uint32_t)g * P.grp_bytes, &tmS2, g * 32, r0, bar);
         }
         if (P.pf_dist) {      // L2 prefetch: stages beyond the ring (the first stage also requests the ones in between)
-          for (int pt = ti == 0 ? P.nstage : ti + P.pf_dist; pt <= ti + P.pf_dist && pt < my_tiles; ++pt) {
+          for (int pt = ti == 0 ? nslots_ : ti + P.pf_dist; pt <= ti + P.pf_dist && pt < my_tiles; ++pt) {
             const int pr = (int)((t_begin + pt) * P.PT);
             for (int g = 0; g < P.Gb; ++g) {
               tma_prefetch_2d(&tmB, g * 32, pr);
@@ -340,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_mn_kernel(const Params P
         }
       }
       __syncwarp();
-      if (++stage == P.nstage) { stage = 0; phase ^= 1u; }
+      if (++stage == nslots_) { stage = 0; phase ^= 1u; }
     }
     }
     // ===================== MMA issuer: lane 0 of warp 0 (the epilogue warps have nothing to do until the end) ==========
@@ -558,19 +591,38 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   P.stage_bytes = P.off_slo + (uint32_t)P.Gs * P.grp_bytes;
   // the last big block reads 4 groups from its first one: stay inside the dynamic shared window
   const uint32_t overrun = (uint32_t)(P.nblocks * 4 - P.Gb) * P.grp_bytes;
-  const size_t tail = 1024 /* alignment slack */ + 256 /* barriers */ + overrun;
-  int nstage = (int)((226 * 1024 - tail) / P.stage_bytes);
-  if (nstage > tcm::MAX_STAGES) nstage = tcm::MAX_STAGES;
-  if (nstage < 2) return -1;
+  const size_t tail = 1024 /* alignment slack */ + 320 /* barriers */ + overrun;
+  auto two_ = [](const TileSrc& s) { return s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS; };
+  P.raw_b2 = (uint32_t)P.Gb * P.grp_bytes;
+  P.raw_s = (uint32_t)(P.Gb * (two_(P.big) ? 2 : 1)) * P.grp_bytes;
+  P.raw_s2 = P.raw_s + (uint32_t)P.Gs * P.grp_bytes;
+  P.raw_bytes = P.raw_s + (uint32_t)(P.Gs * (two_(P.small) ? 2 : 1)) * P.grp_bytes;
+  // C3D_WMN_RAW: 1 = landing ring decoupled from a 2-deep operand ring where at least 2 landing slots fit; 0 (default) in
+  // place.  Measured neutral (277 vs 275 us at res2, 54.97 vs 55.10 ms per step on the same box): with the loads running
+  // ahead the producers wait for operand slots instead of for data -- the per-stage hand-off chain, not the load depth,
+  // sets the rate (profiles/r02_summary.md section 2.2).
+  static const int raw_env = getenv("C3D_WMN_RAW") ? atoi(getenv("C3D_WMN_RAW")) : 0;
+  const size_t budget = 226 * 1024 - tail;
+  int nstage, nraw = 0;
+  if (raw_env && 2 * (size_t)P.stage_bytes + 2 * (size_t)P.raw_bytes <= budget) {
+    nstage = 2;
+    nraw = (int)((budget - 2 * (size_t)P.stage_bytes) / P.raw_bytes);
+    if (nraw > tcm::MAX_STAGES) nraw = tcm::MAX_STAGES;
+  } else {
+    nstage = (int)(budget / P.stage_bytes);
+    if (nstage > tcm::MAX_STAGES) nstage = tcm::MAX_STAGES;
+    if (nstage < 2) return -1;
+  }
   P.nstage = nstage;
-  const size_t smem = (size_t)nstage * P.stage_bytes + tail;
+  P.nraw = nraw;
+  const size_t smem = (size_t)nstage * P.stage_bytes + (size_t)nraw * P.raw_bytes + tail;
   {
     static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : 0;       // 0 off (default), -1 auto, n stages past the ring
     auto two = [](const TileSrc& s) { return s.mode == PRO_BNBWD || s.mode == PRO_ABSDIFF || s.mode == PRO_MASK_POS; };
     const long long raw = (long long)PT * 128 * (P.Gb * (two(P.big) ? 2 : 1) + P.Gs * (two(P.small) ? 2 : 1));
     int d = (int)((128 * 1024 + raw - 1) / raw);
     if (d > 12) d = 12;
-    P.pf_dist = pf_env == 0 ? 0 : nstage + (pf_env < 0 ? d : pf_env);
+    P.pf_dist = pf_env == 0 ? 0 : (nraw > 0 ? nraw : nstage) + (pf_env < 0 ? d : pf_env);
   }
 
   CUtensorMap tmB, tmB2, tmS, tmS2;
@@ -596,8 +648,8 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
     unsigned long long h[32 * 8];
     cudaMemcpyAsync(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
-    fprintf(stderr, "[wmdbg] M=%lld big=%d(mode %d) small=%d(mode %d) nblocks=%d NsP=%d PT=%d nstage=%d smem=%zu\n", M, P.big.K,
-            P.big.mode, P.small.K, P.small.mode, P.nblocks, P.NsP, PT, P.nstage, smem);
+    fprintf(stderr, "[wmdbg] M=%lld big=%d(mode %d) small=%d(mode %d) nblocks=%d NsP=%d PT=%d nstage=%d nraw=%d smem=%zu\n", M, P.big.K,
+            P.big.mode, P.small.K, P.small.mode, P.nblocks, P.NsP, PT, P.nstage, P.nraw, smem);
     for (int w = 0; w < tcm::NTHREADS / 32; ++w) {
       const unsigned long long* o = h + w * 8;
       const char* role = w == 0 ? "mma+epi" : w == 1 ? "tma+epi" : w < 4 ? "epi " : "prod";
