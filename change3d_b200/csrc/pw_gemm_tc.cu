@@ -1003,7 +1003,9 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
   // producer-heavy shapes (a transform with transcendental / two-operand arithmetic in front of a narrow output):
   // one epilogue warpgroup, five producer groups of two warps each.  C3D_TC_HEAVY: 0 off, 1 where the compact kernel
   // does not apply, 2 also instead of the compact kernel, 3 for every shape (tuning aid)
-  static const int heavy_on = getenv("C3D_TC_HEAVY") ? atoi(getenv("C3D_TC_HEAVY")) : 1;
+  // default 0 since round 2: with the cheaper split / folded BN-backward prologues the 8 + 7 kernel is the faster one for
+  // these shapes too (res4 conv_a dgrad 113 -> 90 us, step 54.78 -> 53.83 ms, same box; CC unchanged)
+  static const int heavy_on = getenv("C3D_TC_HEAVY") ? atoi(getenv("C3D_TC_HEAVY")) : 0;
   const bool heavy_shape = (g.a.mode == PRO_BN_GATE_SWISH || g.a.mode == PRO_BNBWD) && g.epi != EPI_SWISH_BWD && g.a.K >= 2 * g.N;
   const bool ok_h = heavy_on && (heavy_shape || heavy_on >= 3) && tc_plan<4, 10, 2>(Ph, 224 * 1024, 128, 4, ns_h, smem_h) && (!ok_b || ns_h <= ns_b);
   if (ok_h && heavy_on >= 2) return tc_launch<4, 10, 2, 1>(Ph, tmA, tmA2, num_sms, ns_h, smem_h, stream);

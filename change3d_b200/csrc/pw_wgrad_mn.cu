@@ -611,6 +611,10 @@ int c3d_launch_pw_wgrad_mn(const TileSrc& p, const TileSrc& q, long long M, floa
   } else {
     nstage = (int)(budget / P.stage_bytes);
     if (nstage > tcm::MAX_STAGES) nstage = tcm::MAX_STAGES;
+    {      // C3D_WMN_STAGES caps the ring (tuning: a shallower ring leaves shared memory to kernels of the other stream)
+      static const int cap_env = getenv("C3D_WMN_STAGES") ? atoi(getenv("C3D_WMN_STAGES")) : tcm::MAX_STAGES;
+      if (cap_env >= 2 && nstage > cap_env) nstage = cap_env;
+    }
     if (nstage < 2) return -1;
   }
   P.nstage = nstage;

@@ -147,3 +147,17 @@ class GpuAugment:
         img_f = torch.cat([pre, post], 1).permute(0, 2, 3, 1).contiguous()
         lab_u8 = lab.permute(0, 2, 3, 1).to(torch.uint8).contiguous() if lab is not None else None
         return self._launch(img_f, lab_u8, params, self.H, self.W, Lc)
+
+
+def is_raw_batch(batch) -> bool:
+    """True for batches of raw pairs (img uint8 (B, Hs, Ws, 6), label uint8) -- what a dataset yields when it leaves the
+    transform chain to the GPU -- as opposed to the reference's float (B, 6, H, W) tensors."""
+    img = batch[0]
+    return img.dtype == torch.uint8 and img.dim() == 4 and img.shape[-1] == 6
+
+
+def augment_raw_batch(batch, task: str, in_height: int, in_width: int, train: bool):
+    """(img_u8, label_u8) on the device -> (pre, post, label) through GpuAugment, decisions drawn for this batch."""
+    img, label = batch[0], batch[1]
+    params = draw_params(img.shape[0], in_width, task, train)
+    return GpuAugment(in_height, in_width, task)(img, label, params)

@@ -31,7 +31,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .input_pipeline import DevicePrefetcher
+from .input_pipeline import DevicePrefetcher, augment_raw_batch, is_raw_batch
 from .losses import bce_dice_loss
 from .metrics import cm2score
 from .model.trainer import Trainer
@@ -110,9 +110,12 @@ def make_loaders(args, world: int, rank: int, datasets=None):
     return train_loader, val_loader, test_loader, len(train_loader)
 
 
-def _split(batch):
+def _split(batch, args=None, train: bool = False):
     """(img (B,6,H,W), target) already on the device -> pre, post, target as the scripts slice them
-    (scripts/train_BCD.py:182-185), contiguous fp32."""
+    (scripts/train_BCD.py:182-185), contiguous fp32.  Raw uint8 batches (img (B,Hs,Ws,6), label (B,Hs,Ws)) go through the
+    GPU transform chain instead (input_pipeline.GpuAugment: data/transforms.py on the device; 4x fewer H2D bytes)."""
+    if args is not None and is_raw_batch(batch):
+        return augment_raw_batch(batch, "bcd", args.in_height, args.in_width, train)
     img, target = batch
     return img[:, 0:3].float().contiguous(), img[:, 3:6].float().contiguous(), target.float()
 
@@ -126,7 +129,7 @@ def val(args, val_loader, model, epoch, dev):
     loss_sum = torch.zeros((), dtype=torch.float32, device=dev)
     n = 0
     for batch in DevicePrefetcher(val_loader, dev):          # pinned batches staged one ahead on a copy stream
-        pre, post, target = _split(batch)
+        pre, post, target = _split(batch, args, train=False)
         output = model.update_bcd(pre, post)
         loss_sum += bce_dice_loss(output, target, cm=cm)
         n += 1
@@ -144,7 +147,7 @@ def train(args, train_loader, step: BCDTrainStep, epoch: int, max_batches: int, 
     n = 0
     t_epoch = time.time()
     for iter_idx, batch in enumerate(DevicePrefetcher(train_loader, dev)):
-        pre, post, target = _split(batch)
+        pre, post, target = _split(batch, args, train=True)
         lr = adjust_learning_rate(args, step.opt, epoch, iter_idx + cur_iter, max_batches, lr_factor=lr_factor)
         if pre.shape[0] != full and step.use_graph:
             # ragged last batch (drop_last=False in the reference): static-shape graph does not apply
