@@ -285,9 +285,11 @@ def block_bwd_stat_doubles(N: int, ci: int, cout: int, has_bn1: bool) -> int:
     return 2 * cout + (2 * cout if has_bn1 else 0) + 2 * N * cis + 2 * cis
 
 
-def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena, ga: GradArena):
+def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena, ga: GradArena, pending: Optional[list] = None):
     """Backward of one ResBlock.  dOut: (N,T,OH,OW,Cout) dense.  Returns dx (N,T,H,W,Cin); parameter
-    gradients are written into `ga` in ResBlock.param_list() order."""
+    gradients are written into `ga` in ResBlock.param_list() order.  `pending`: when given, the side stream is NOT
+    joined at the end of the block; the tensors its weight-gradient kernels still read are appended to the list and the
+    caller joins later (res_stage_backward), so that those kernels may overlap the next blocks' dgrad chain too."""
     N, T, H, W, OH, OW, Cin, Ci, Cis, Cout = s.dims
     b2 = blk.branch2
     dev = dOut.device
@@ -366,7 +368,10 @@ def res_block_backward(blk, s: BlockSaved, dOut: torch.Tensor, arena: StatArena,
     ops.pw_gemm(P_a, b2.conv_a.weight, w_sr=Cin, w_so=1, Kred=Ci, N=Cin, Ns=Cin, M=M_in, Y=dx, epi=EPI_ADD2,
                 E1=None if first else d_pre, E2=dx1)
     if side is not None:
-        main.wait_stream(side)                      # join before this block's tensors can be released
+        if pending is not None:
+            pending.append((s, d_pre, coef_c, dr, coef_a))     # keep what the side stream reads alive until the join
+        else:
+            main.wait_stream(side)                  # join before this block's tensors can be released
     else:
         ops.pw_wgrad(P_a, Q_a, M=M_in, dW=g_wa, dw_sn=Cin, dw_sk=1, N=Ci, K=Cin)
     return dx
@@ -389,10 +394,18 @@ def res_stage_backward(stage, saved: List[BlockSaved], g: torch.Tensor):
     starts = [0]
     for c in counts[:-1]:
         starts.append(starts[-1] + c)
+    # side-stream join every C3D_JOIN_EVERY blocks (default 1 = after every block) and at the end of the stage
+    join_every = int(os.environ.get("C3D_JOIN_EVERY", "1"))
+    side = _side_stream()
+    pending: list = []
     for bi in range(len(stage.res_blocks) - 1, -1, -1):
         ga.i = starts[bi]
-        g = res_block_backward(stage.res_blocks[bi], saved[bi], g, arena, ga)
-        saved[bi] = None          # release this block's activations
+        defer = side is not None and join_every > 1
+        g = res_block_backward(stage.res_blocks[bi], saved[bi], g, arena, ga, pending if defer else None)
+        saved[bi] = None          # release this block's activations (deferred joins keep them in `pending`)
+        if defer and (len(pending) >= join_every or bi == 0):
+            torch.cuda.current_stream().wait_stream(side)
+            pending.clear()
     return g, ga.returned()
 
 

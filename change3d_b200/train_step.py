@@ -21,6 +21,8 @@ flat buffer with the clamp fused into its Adam launch.
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -239,8 +241,13 @@ class TrainStep:
         from . import _lib
         n0 = _lib.LAUNCHES[0]
         self.graph = torch.cuda.CUDAGraph()
+        # The capture stream is a HIGH-priority stream: the kernel nodes of the dgrad chain inherit it, the weight-gradient
+        # kernels forked onto engine._side_stream() (default priority) do not, so whenever both have thread blocks pending
+        # the block scheduler places the critical path first (C3D_GRAPH_PRIORITY=0: default-priority capture stream).
+        prio = -1 if os.environ.get("C3D_GRAPH_PRIORITY", "1") == "1" else 0
+        cap_stream = torch.cuda.Stream(priority=prio)
         # thread_local: a DataLoader pin-memory thread may call cudaHostAlloc while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode="thread_local"):
             self.loss = self._iteration(*self.static)
         self.captured_launches = _lib.LAUNCHES[0] - n0 + self.adam_launches      # + the Adam launch(es) outside the graph
         if getattr(self, "cm", None) is not None:
