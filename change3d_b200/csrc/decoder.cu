@@ -5,6 +5,8 @@
 // positions per input pixel, U[j][i][ky][kx][co] = sum_ci t[j][i][ci] W[ci][co][ky][kx], and the col2im gather
 // below (output pixel (y, x) sums the 4 positions with 2j-1+ky = y, 2i-1+kx = x, plus bias and the skip tensor);
 // the backward uses the mirrored im2col so that d t and d W are dense GEMMs as well (tcgen05 kernels).
+#include <stdlib.h>
+
 #include "c3d_common.cuh"
 #include "../../include/change3d_b200.h"
 
@@ -55,10 +57,95 @@ __global__ void __launch_bounds__(256) dec_head_fwd_kernel(const float* __restri
   }
 }
 
+
+// C = 24 fast path (the Change3D decoders): tile + halo staged in shared memory with whole-sector loads (the kernel
+// above reads its 9 x 24 inputs per pixel straight from global memory at a 96-byte lane stride: 32 sectors per
+// request, and its class loop is predicated on a runtime bound -- ncu: 87 % issue-active, 246 M warp instructions
+// for 0.45 G FMA).  NCLS is a template parameter; one thread per output pixel.
+#define HEAD_XLD 28
+template <int NCLS>
+__global__ void __launch_bounds__(256) dec_head_fwd24_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                             float* __restrict__ Y, int H, int W, int apply_sigmoid) {
+  constexpr int C = 24, NQ = 6, PW = 34, PH = 10, NPIX = PW * PH;
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                         // [9][NCLS][24]
+  float* xs = ws + 9 * NCLS * C;          // [NPIX][HEAD_XLD]
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z, h0 = blockIdx.y * 8, w0 = blockIdx.x * 32;
+  for (int i = tid; i < 9 * NCLS * C; i += 256) {
+    const int c = i % C, k = (i / C) % NCLS, tap = i / (C * NCLS);
+    ws[i] = __ldg(w + (k * C + c) * 9 + tap);
+  }
+  for (int i = tid; i < NPIX * NQ; i += 256) {
+    const int p = i / NQ, q = i - p * NQ, y = p / PW, x = p - y * PW;
+    const int h = h0 - 1 + y, ww = w0 - 1 + x;
+    float4 v = f4zero();
+    if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
+    *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v;
+  }
+  __syncthreads();
+  const int lx = tid & 31, ly = tid >> 5;
+  const int ow = w0 + lx, oh = h0 + ly;
+  if (ow >= W || oh >= H) return;
+  float acc[NCLS];
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float* xp = xs + ((ly + kh) * PW + lx + kw) * HEAD_XLD;
+      const float* wp = ws + (kh * 3 + kw) * NCLS * C;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(xp + 4 * q);
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + k * C + 4 * q);
+          acc[k] = fmaf(x.x, wv.x, fmaf(x.y, wv.y, fmaf(x.z, wv.z, fmaf(x.w, wv.w, acc[k]))));
+        }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+    float v = acc[k];
+    if (apply_sigmoid) v = 1.0f / (1.0f + expf(-v));
+    Y[(((long long)n * NCLS + k) * H + oh) * W + ow] = v;
+  }
+}
+
+template <int NCLS>
+static int launch_head_fwd24(const float* X, const float* w, float* Y, int B, int H, int W, int apply_sigmoid, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+  const size_t smem = (size_t)(9 * NCLS * 24 + 340 * HEAD_XLD) * sizeof(float);
+  if (cudaFuncSetAttribute(dec_head_fwd24_kernel<NCLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return C3D_ERR_SMEM;
+  dec_head_fwd24_kernel<NCLS><<<grid, 256, smem, st>>>(X, w, Y, H, W, apply_sigmoid);
+  return c3d_check_last(cudaGetLastError());
+}
+
+static bool head_fast_path() {
+  const char* v = getenv("C3D_HEAD_FAST");      // 0: the generic kernels (any C, runtime class count)
+  return !v || atoi(v) != 0;
+}
+
 extern "C" int c3d_dec_head_fwd(const float* X, const float* w, float* Y, int B, int H, int W, int C, int ncls,
                                 int apply_sigmoid, void* stream_) {
   if (!X || !w || !Y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || ncls <= 0 || ncls > HEAD_MAX_CLS)
     return C3D_ERR_ARG;
+  if (C == 24 && head_fast_path()) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    switch (ncls) {
+      case 1: return launch_head_fwd24<1>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 2: return launch_head_fwd24<2>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 3: return launch_head_fwd24<3>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 4: return launch_head_fwd24<4>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 5: return launch_head_fwd24<5>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 6: return launch_head_fwd24<6>(X, w, Y, B, H, W, apply_sigmoid, st);
+      case 7: return launch_head_fwd24<7>(X, w, Y, B, H, W, apply_sigmoid, st);
+      default: return launch_head_fwd24<8>(X, w, Y, B, H, W, apply_sigmoid, st);
+    }
+  }
   dim3 grid((W + 31) / 32, (H + 7) / 8, B);
   size_t smem = (size_t)9 * ncls * C * sizeof(float);
   dec_head_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(X, w, Y, H, W, C, ncls, apply_sigmoid);
@@ -71,8 +158,6 @@ extern "C" int c3d_dec_head_fwd(const float* X, const float* w, float* Y, int B,
 //   dW[k][ci][tap] += sum_o dlogit[o][k] * X[o + off(tap)][ci]
 // Persistent CTAs over 32x8 tiles; dlogit and X tiles (with a 1-pixel halo) staged in shared memory.
 // ------------------------------------------------------------------------------------------------
-#define HEAD_XLD 28
-
 __global__ void __launch_bounds__(256) dec_head_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ pred,
                                                            const float* __restrict__ X, const float* __restrict__ w,
                                                            float* __restrict__ dX, float* __restrict__ dW, int B, int H,
@@ -167,6 +252,146 @@ __global__ void __launch_bounds__(256) dec_head_bwd_kernel(const float* __restri
   }
 }
 
+
+// C = 24 fast path of the head backward.  ncu on the kernel above: 240 M warp instructions, barrier + wait stalls --
+// its loops run over runtime bounds, the weight gradient of a 1-class head is owned by 54 of the 256 threads, and
+// the dgrad pass issues two LDS per 4 FMA.  Here: the class count is a template parameter; the dgrad pass loads one
+// dlogit per (tap, class) and sweeps the 6 channel quads (7 LDS per 24 FMA); a weight-gradient thread owns one
+// (class, channel quad) with all 9 taps in registers and walks 8-pixel row segments with a sliding 3 x 3 window of
+// input quads (3 LDS.128 + 1 LDS per 36 FMA); the segments of a tile are spread over 256 / (6 NCLS) threads per owner.
+template <int NCLS>
+__global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __restrict__ dpred, const float* __restrict__ pred,
+                                                                const float* __restrict__ X, const float* __restrict__ w,
+                                                                float* __restrict__ dX, float* __restrict__ dW, int B, int H,
+                                                                int W, int is_sigmoid) {
+  constexpr int C = 24, NQ = 6, PW = 34, PH = 10, NPIX = PW * PH;
+  constexpr int NI = NCLS * NQ;                                // (class, quad) owners
+  constexpr int TP = (256 / NI) > 32 ? 32 : (256 / NI);        // threads per owner; a tile has 32 segments of 8 pixels
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                        // [9][NCLS][24]
+  float* red = ws + 9 * NCLS * C;        // [NCLS][24][9] weight-gradient reduction (end of the launch)
+  float* dl = red + 9 * NCLS * C;        // [NCLS][NPIX]
+  float* xs = dl + ((NCLS * NPIX + 3) & ~3);   // [NPIX][HEAD_XLD]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 9 * NCLS * C; i += 256) {
+    const int c = i % C, k = (i / C) % NCLS, tap = i / (C * NCLS);
+    ws[i] = __ldg(w + (k * C + c) * 9 + tap);
+    red[i] = 0.f;
+  }
+  const int owner = tid / TP, sub = tid - owner * TP;
+  const bool wg_active = owner < NI;
+  const int wk = owner / NQ, wq = owner - wk * NQ;
+  float4 wacc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wacc[t] = f4zero();
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8, ntiles = tiles_x * tiles_y * B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int trem = tile - n * tiles_x * tiles_y;
+    const int h0 = (trem / tiles_x) * 8, w0 = (trem % tiles_x) * 32;
+    __syncthreads();
+    for (int i = tid; i < NCLS * NPIX; i += 256) {
+      const int k = i / NPIX, p = i - k * NPIX, y = p / PW, x = p - y * PW;
+      const int h = h0 - 1 + y, ww = w0 - 1 + x;
+      float v = 0.f;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) {
+        const long long off = (((long long)n * NCLS + k) * H + h) * W + ww;
+        v = __ldg(dpred + off);
+        if (is_sigmoid) { const float p_ = __ldg(pred + off); v *= p_ * (1.f - p_); }
+      }
+      dl[i] = v;
+    }
+    for (int i = tid; i < NPIX * NQ; i += 256) {
+      const int p = i / NQ, q = i - p * NQ, y = p / PW, x = p - y * PW;
+      const int h = h0 - 1 + y, ww = w0 - 1 + x;
+      float4 v = f4zero();
+      if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
+      *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v;
+    }
+    __syncthreads();
+    {  // dgrad: one thread per interior pixel; dX[i] = sum_{k,tap} w[k][.][tap] * dlogit[i - off(tap)][k]
+      const int lx = tid & 31, ly = tid >> 5;
+      const int h = h0 + ly, ww = w0 + lx;
+      if (h < H && ww < W) {
+        float4 acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = f4zero();
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int p = (ly + 2 - kh) * PW + (lx + 2 - kw);
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) {
+              const float d = dl[k * NPIX + p];
+              const float* wp = ws + ((kh * 3 + kw) * NCLS + k) * C;
+#pragma unroll
+              for (int q = 0; q < NQ; ++q) {
+                const float4 wv = *reinterpret_cast<const float4*>(wp + 4 * q);
+                acc[q].x = fmaf(d, wv.x, acc[q].x); acc[q].y = fmaf(d, wv.y, acc[q].y);
+                acc[q].z = fmaf(d, wv.z, acc[q].z); acc[q].w = fmaf(d, wv.w, acc[q].w);
+              }
+            }
+          }
+        float* o = dX + (((long long)n * H + h) * W + ww) * C;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) st4(o + 4 * q, acc[q]);
+      }
+    }
+    if (wg_active) {  // dW[k][ci][tap] += sum_o dlogit[o][k] * X[o + off(tap)][ci]
+      for (int seg = sub; seg < 32; seg += TP) {
+        const int row = seg >> 2, xs0 = (seg & 3) * 8;
+        const float* xb = xs + (row * PW + xs0) * HEAD_XLD + 4 * wq;       // halo (row + kh, xs0 + i + kw)
+        const float* db = dl + wk * NPIX + (row + 1) * PW + xs0 + 1;
+        float4 win[3][3];                                                     // [column mod 3][kh]
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) win[j][kh] = *reinterpret_cast<const float4*>(xb + (kh * PW + j) * HEAD_XLD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+            win[(i + 2) % 3][kh] = *reinterpret_cast<const float4*>(xb + (kh * PW + i + 2) * HEAD_XLD);
+          const float d = db[i];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float4 xv = win[(i + kw) % 3][kh];
+              float4& a = wacc[kh * 3 + kw];
+              a.x = fmaf(d, xv.x, a.x); a.y = fmaf(d, xv.y, a.y); a.z = fmaf(d, xv.z, a.z); a.w = fmaf(d, xv.w, a.w);
+            }
+        }
+      }
+    }
+  }
+  if (wg_active) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float* r = red + ((wk * C + 4 * wq) * 9) + t;
+      atomicAdd(r, wacc[t].x); atomicAdd(r + 9, wacc[t].y); atomicAdd(r + 18, wacc[t].z); atomicAdd(r + 27, wacc[t].w);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * NCLS * C; i += 256) atomicAdd(dW + i, red[i]);
+}
+
+template <int NCLS>
+static int launch_head_bwd24(const float* dpred, const float* pred, const float* X, const float* w, float* dX, float* dW,
+                             int B, int H, int W, int is_sigmoid, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * 9 * NCLS * 24 + ((NCLS * 340 + 3) & ~3) + 340 * HEAD_XLD) * sizeof(float);
+  if (cudaFuncSetAttribute(dec_head_bwd24_kernel<NCLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return C3D_ERR_SMEM;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = ((W + 31) / 32) * ((H + 7) / 8) * B;
+  const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
+  dec_head_bwd24_kernel<NCLS><<<grid, 256, smem, st>>>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid);
+  return c3d_check_last(cudaGetLastError());
+}
+
 extern "C" int c3d_dec_head_bwd(const float* dpred, const float* pred, const float* X, const float* w, float* dX,
                                 float* dW, int B, int H, int W, int C, int ncls, int is_sigmoid, void* stream_) {
   if (!dpred || !X || !w || !dX || !dW || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || C > 24 || ncls <= 0 ||
@@ -174,6 +399,19 @@ extern "C" int c3d_dec_head_bwd(const float* dpred, const float* pred, const flo
     return C3D_ERR_ARG;
   if (is_sigmoid && !pred) return C3D_ERR_ARG;
   if (ncls * (C >> 2) * 9 > 512) return C3D_ERR_ARG;
+  if (C == 24 && head_fast_path()) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    switch (ncls) {
+      case 1: return launch_head_bwd24<1>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 2: return launch_head_bwd24<2>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 3: return launch_head_bwd24<3>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 4: return launch_head_bwd24<4>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 5: return launch_head_bwd24<5>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 6: return launch_head_bwd24<6>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      case 7: return launch_head_bwd24<7>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+      default: return launch_head_bwd24<8>(dpred, pred, X, w, dX, dW, B, H, W, is_sigmoid, st);
+    }
+  }
   const size_t smem = (size_t)(9 * ncls * C + ncls * 340 + 340 * HEAD_XLD) * sizeof(float);
   cudaFuncSetAttribute(dec_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;

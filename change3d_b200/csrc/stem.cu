@@ -2,6 +2,8 @@
 // (model/trainer.py:154-162): [pre, P perception frames, post] -> Conv3d 1x3x3 (3->24, pad 0,1,1)
 // -> depthwise Conv3d 5x1x1 (pad 2,0,0) -> raw NDHWC output + BatchNorm statistics.
 // pytorchvideo's Conv2plus1d runs the module stored as conv_t (the spatial conv) first.
+#include <stdlib.h>
+
 #include "c3d_common.cuh"
 #include "../../include/change3d_b200.h"
 
@@ -97,6 +99,126 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemFrames fr, cons
   }
 }
 
+// Stem forward, second form (default; C3D_STEM_FWD=0 selects the kernel above).  ncu on the quad-per-thread kernel:
+// 332 M warp instructions, shared-memory pipe 56 %, 32 sectors per store request, 40 shuffles per thread and channel
+// quad for the statistics.  Here a thread owns ONE CHANNEL (27 + 5 weights in registers) and a strip of four
+// horizontally adjacent pixels: the six input columns of a (frame, ci, kh) row arrive as three LDS.64 and feed 12 FMA;
+// 24 consecutive lanes store the 24 channels of a pixel (whole sectors); the BatchNorm sums stay in per-thread
+// registers (fp32 within a tile, fp64 across the tiles of a persistent CTA) and are reduced once per launch.
+template <int T, int NSLOT>
+__global__ void __launch_bounds__(NSLOT * STEM_C) stem_fwd_pc_kernel(const StemFrames fr, const float* __restrict__ wxy,
+                                                                      const float* __restrict__ wt, float* __restrict__ Y,
+                                                                      double* __restrict__ stats, int B, int H, int W) {
+  constexpr int NT = NSLOT * STEM_C;
+  constexpr int PW = STEM_TW + 2, PH = STEM_TH + 2, NPIX = PW * PH, PWP = STEM_TW + 4;
+  constexpr int NSTRIP = (STEM_TW / 4) * STEM_TH;
+  __shared__ __align__(16) float patch[T * 3 * PH * PWP];
+  __shared__ double s_red[2 * STEM_C];
+  const int tid = threadIdx.x;
+  const int c = tid % STEM_C, slot = tid / STEM_C;
+  float wr[27], wtr[5];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) wr[j] = __ldg(wxy + c * 27 + j);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) wtr[k] = __ldg(wt + c * 5 + k);
+  if (tid < 2 * STEM_C) s_red[tid] = 0.0;
+  double dsum = 0.0, dsq = 0.0;
+  const long long fstride = (long long)H * W * STEM_C;
+  const int tiles_x = (W + STEM_TW - 1) / STEM_TW, tiles_y = (H + STEM_TH - 1) / STEM_TH;
+  const int ntiles = tiles_x * tiles_y * B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int trem = tile - n * tiles_x * tiles_y;
+    const int h0 = (trem / tiles_x) * STEM_TH, w0 = (trem % tiles_x) * STEM_TW;
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < T; ++f) {
+      const float* fp = fr.p[f] + n * fr.sn[f];
+      const long long fsc = fr.sc[f];
+      for (int i = tid; i < 3 * NPIX; i += NT) {
+        const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+        const int h = h0 - 1 + y, w = w0 - 1 + x;
+        float v = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(fp + ci * fsc + (long long)h * W + w);
+        patch[((f * 3 + ci) * PH + y) * PWP + x] = v;
+      }
+    }
+    __syncthreads();
+    float psum = 0.f, psq = 0.f;
+    float* ybase = Y + (long long)n * T * fstride + c;
+    for (int sp = slot; sp < NSTRIP; sp += NSLOT) {
+      const int ly = sp / (STEM_TW / 4), x0 = 4 * (sp - ly * (STEM_TW / 4));
+      const int h = h0 + ly, w = w0 + x0;
+      if (h >= H || w >= W) continue;
+      float sacc[T][4];
+#pragma unroll
+      for (int f = 0; f < T; ++f)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sacc[f][i] = 0.f;
+      const float* prow = patch + ly * PWP + x0;
+#pragma unroll
+      for (int f = 0; f < T; ++f)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* r = prow + ((f * 3 + ci) * PH + kh) * PWP;
+            const float2 a = *reinterpret_cast<const float2*>(r), b = *reinterpret_cast<const float2*>(r + 2),
+                         e = *reinterpret_cast<const float2*>(r + 4);
+            const float in[6] = {a.x, a.y, b.x, b.y, e.x, e.y};
+            const int j = ci * 9 + kh * 3;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sacc[f][i] = fmaf(in[i + kw], wr[j + kw], sacc[f][i]);
+          }
+      float* yp = ybase + ((long long)h * W + w) * STEM_C;
+#pragma unroll
+      for (int to = 0; to < T; ++to) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int f = 0; f < T; ++f) {
+          const int tap = f - to + 2;
+          if (tap < 0 || tap > 4) continue;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = fmaf(wtr[tap], sacc[f][i], o[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (w + i < W) {
+            yp[to * fstride + i * STEM_C] = o[i];
+            psum += o[i];
+            psq = fmaf(o[i], o[i], psq);
+          }
+        }
+      }
+    }
+    dsum += (double)psum;
+    dsq += (double)psq;
+  }
+  if (stats) {
+    atomicAdd(&s_red[c], dsum);
+    atomicAdd(&s_red[STEM_C + c], dsq);
+    __syncthreads();
+    if (tid < 2 * STEM_C) atomicAdd(stats + tid, s_red[tid]);
+  }
+}
+
+template <int T>
+static int launch_stem_fwd_pc(const StemFrames& fr, const float* wxy, const float* wt, float* Y, double* stats, int B, int H,
+                              int W, cudaStream_t st) {
+  constexpr int NSLOT = 8;
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_fwd_pc_kernel<T, NSLOT>, NSLOT * STEM_C, 0);
+  if (per_sm < 1) per_sm = 1;
+  const int ntiles = ((W + STEM_TW - 1) / STEM_TW) * ((H + STEM_TH - 1) / STEM_TH) * B;
+  const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
+  stem_fwd_pc_kernel<T, NSLOT><<<grid, NSLOT * STEM_C, 0, st>>>(fr, wxy, wt, Y, stats, B, H, W);
+  return c3d_check_last(cudaGetLastError());
+}
+
 static int stem_frames(StemFrames& fr, const float* const* frame_ptr, const long long* stride_n,
                        const long long* stride_c, int T) {
   if (!frame_ptr || !stride_n || !stride_c || T < 3 || T > 5) return C3D_ERR_ARG;
@@ -117,6 +239,15 @@ extern "C" int c3d_stem_fwd(const float* const* frame_ptr, const long long* stri
   if (int e = stem_frames(fr, frame_ptr, stride_n, stride_c, T)) return e;
   dim3 grid((W + STEM_TW - 1) / STEM_TW, (H + STEM_TH - 1) / STEM_TH, B);
   cudaStream_t st = (cudaStream_t)stream_;
+  const char* m = getenv("C3D_STEM_FWD");
+  if (!m || atoi(m) != 0) {
+    switch (T) {
+      case 3: return launch_stem_fwd_pc<3>(fr, w_xy, w_t, Y, stats, B, H, W, st);
+      case 4: return launch_stem_fwd_pc<4>(fr, w_xy, w_t, Y, stats, B, H, W, st);
+      case 5: return launch_stem_fwd_pc<5>(fr, w_xy, w_t, Y, stats, B, H, W, st);
+      default: return C3D_ERR_ARG;
+    }
+  }
   switch (T) {
     case 3: stem_fwd_kernel<3><<<grid, 256, 0, st>>>(fr, w_xy, w_t, Y, stats, H, W); break;
     case 4: stem_fwd_kernel<4><<<grid, 256, 0, st>>>(fr, w_xy, w_t, Y, stats, H, W); break;
@@ -333,12 +464,246 @@ static int launch_stem_bwd_tile(const StemFrames& fr, const float* dpre, const f
   return c3d_check_last(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem backward, second form (default).  ncu on the kernel above (profiles/r02_summary.md section 2.5): shared-memory
+// pipe at 81 % of its peak, short-scoreboard + barrier stalls, 754 M warp instructions -- one LDS per 2-3 FMA in the
+// spatial-conv recompute and in the dwxy pass, three roles run one after the other on 252 / 162 / 128 of 256 threads.
+// Here a thread owns ONE CHANNEL and walks pairs of horizontally adjacent pixels:
+//   * its 27 spatial weights, 27 dwxy accumulators, 5 temporal weights and 5 dwt accumulators live in registers for
+//     the whole launch (no weight loads, no weight-gradient traffic inside the loop);
+//   * the 4 input columns a pixel pair needs per (frame, ci, kh) arrive as two LDS.64 and feed 12 FMA: the recompute
+//     of s AND the dwxy accumulation use the same values (54 LDS.64 per 324 FMA instead of 135 LDS per 324);
+//   * d_pre / y are read as 24 consecutive floats per pixel by 24 consecutive lanes (whole sectors);
+//   * ds is written to shared memory for the perception frames only, tile + halo; the halo ring is computed by light
+//     work items (BN backward + temporal transpose, no spatial work); the perception-frame gradient is the last
+//     phase, one thread per pixel pair (4 ds columns x 9 weight quads per (kh, q): 13 LDS.128 per 72 FMA).
+// ------------------------------------------------------------------------------------------------
+template <int T, int BTW, int BTH, int NSLOT>
+__global__ void __launch_bounds__(NSLOT * STEM_C, 2)
+stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const float* __restrict__ ys,
+                   const float* __restrict__ bnp, const float* __restrict__ coef, const float* __restrict__ wxy,
+                   const float* __restrict__ wt, float* __restrict__ dwxy, float* __restrict__ dwt,
+                   float* __restrict__ dperc, int B, int H, int W) {
+  constexpr int P = T - 2;
+  constexpr int NT = NSLOT * STEM_C;
+  constexpr int PW = BTW + 2, PH = BTH + 2, NPIX = PW * PH;
+  constexpr int PWP = BTW + 4;                       // even patch row stride: LDS.64 at even columns
+  constexpr int NPP = (BTW / 2) * BTH;               // interior pixel pairs
+  constexpr int NHALO = 2 * PW + 2 * BTH;            // halo ring pixels
+  static_assert(NPP <= NT, "one thread per pixel pair in the perception-frame pass");
+  extern __shared__ __align__(16) float sm[];
+  float* patch = sm;                                 // [T][3][PH][PWP]
+  float* dsp = patch + T * 3 * PH * PWP;             // [P][NPIX][STEM_DSLD]
+  float* s_wxy = dsp + P * NPIX * STEM_DSLD;         // [27][24]
+  float* s_red = s_wxy + 27 * STEM_C;                // [32][24]: dwxy rows 0..26, dwt rows 27..31
+  const int tid = threadIdx.x;
+  const int c = tid % STEM_C, slot = tid / STEM_C;
+  for (int i = tid; i < 27 * STEM_C; i += NT) { int k = i / STEM_C, cc = i - k * STEM_C; s_wxy[i] = __ldg(wxy + cc * 27 + k); }
+  for (int i = tid; i < 32 * STEM_C; i += NT) s_red[i] = 0.f;
+  float wr[27], acc[27], wtr[5], dwt_acc[5];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) { wr[j] = __ldg(wxy + c * 27 + j); acc[j] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { wtr[k] = __ldg(wt + c * 5 + k); dwt_acc[k] = 0.f; }
+  const float mean = __ldg(bnp + c), rstd = __ldg(bnp + STEM_C + c), scale = __ldg(bnp + 2 * STEM_C + c);
+  const float c1 = __ldg(coef + c), c2 = __ldg(coef + STEM_C + c);
+  const long long fstride = (long long)H * W * STEM_C;          // one frame of d_pre / y
+
+  const int tiles_x = (W + BTW - 1) / BTW, tiles_y = (H + BTH - 1) / BTH;
+  const int ntiles = tiles_x * tiles_y * B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int trem = tile - n * tiles_x * tiles_y;
+    const int h0 = (trem / tiles_x) * BTH, w0 = (trem % tiles_x) * BTW;
+    const float* dbase = dpre + (long long)n * T * fstride + c;
+    const float* ybase = ys + (long long)n * T * fstride + c;
+    __syncthreads();                                            // previous tile's perception pass is done
+#pragma unroll
+    for (int f = 0; f < T; ++f) {                               // static f: the frame table stays in the parameter bank
+      const float* fp = fr.p[f] + n * fr.sn[f];
+      const long long fsc = fr.sc[f];
+      for (int i = tid; i < 3 * NPIX; i += NT) {
+        const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+        const int h = h0 - 1 + y, w = w0 - 1 + x;
+        float v = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(fp + ci * fsc + (long long)h * W + w);
+        patch[((f * 3 + ci) * PH + y) * PWP + x] = v;
+      }
+    }
+    if (dperc) {
+      // halo ring: ds of the perception frames only
+      for (int hp = slot; hp < NHALO; hp += NSLOT) {
+        int y, x;
+        if (hp < PW) { y = 0; x = hp; }
+        else if (hp < 2 * PW) { y = PH - 1; x = hp - PW; }
+        else { const int r = hp - 2 * PW; y = 1 + (r >> 1); x = (r & 1) ? PW - 1 : 0; }
+        const int h = h0 - 1 + y, w = w0 - 1 + x;
+        float dy[T];
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          const long long off = ((long long)h * W + w) * STEM_C;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const float d = __ldg(dbase + t * fstride + off), yv = __ldg(ybase + t * fstride + off);
+            dy[t] = scale * (d - c1 - (yv - mean) * rstd * c2);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < T; ++t) dy[t] = 0.f;
+        }
+#pragma unroll
+        for (int f = 1; f <= P; ++f) {
+          float o = 0.f;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int tap = f - t + 2;
+            if (tap < 0 || tap > 4) continue;
+            o = fmaf(wtr[tap], dy[t], o);
+          }
+          dsp[((f - 1) * NPIX + y * PW + x) * STEM_DSLD + c] = o;
+        }
+      }
+    }
+    __syncthreads();                                            // patch complete
+    for (int pp = slot; pp < NPP; pp += NSLOT) {
+      const int ly = pp / (BTW / 2), x0 = 2 * (pp - ly * (BTW / 2));
+      const int h = h0 + ly, w = w0 + x0;
+      const bool v0 = (h < H && w < W), v1 = (h < H && w + 1 < W);
+      const long long off = ((long long)h * W + w) * STEM_C;
+      float dy[T][2], ds[T][2], s[T][2];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float d0 = 0.f, y0 = 0.f, d1 = 0.f, y1 = 0.f;
+        if (v0) { d0 = __ldg(dbase + t * fstride + off); y0 = __ldg(ybase + t * fstride + off); }
+        if (v1) { d1 = __ldg(dbase + t * fstride + off + STEM_C); y1 = __ldg(ybase + t * fstride + off + STEM_C); }
+        dy[t][0] = v0 ? scale * (d0 - c1 - (y0 - mean) * rstd * c2) : 0.f;
+        dy[t][1] = v1 ? scale * (d1 - c1 - (y1 - mean) * rstd * c2) : 0.f;
+      }
+#pragma unroll
+      for (int f = 0; f < T; ++f) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int tap = f - t + 2;
+          if (tap < 0 || tap > 4) continue;
+          o0 = fmaf(wtr[tap], dy[t][0], o0);
+          o1 = fmaf(wtr[tap], dy[t][1], o1);
+        }
+        ds[f][0] = o0; ds[f][1] = o1;
+        s[f][0] = 0.f; s[f][1] = 0.f;
+        if (f >= 1 && f <= P) {
+          float* q = dsp + ((f - 1) * NPIX + (ly + 1) * PW + x0 + 1) * STEM_DSLD + c;
+          q[0] = o0; q[STEM_DSLD] = o1;
+        }
+      }
+      const float* prow = patch + ly * PWP + x0;
+#pragma unroll
+      for (int f = 0; f < T; ++f)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* r = prow + ((f * 3 + ci) * PH + kh) * PWP;
+            const float2 a = *reinterpret_cast<const float2*>(r), b = *reinterpret_cast<const float2*>(r + 2);
+            const int j = ci * 9 + kh * 3;
+            s[f][0] = fmaf(a.x, wr[j], s[f][0]);     s[f][1] = fmaf(a.y, wr[j], s[f][1]);
+            s[f][0] = fmaf(a.y, wr[j + 1], s[f][0]); s[f][1] = fmaf(b.x, wr[j + 1], s[f][1]);
+            s[f][0] = fmaf(b.x, wr[j + 2], s[f][0]); s[f][1] = fmaf(b.y, wr[j + 2], s[f][1]);
+            acc[j] = fmaf(ds[f][0], a.x, acc[j]);         acc[j] = fmaf(ds[f][1], a.y, acc[j]);
+            acc[j + 1] = fmaf(ds[f][0], a.y, acc[j + 1]); acc[j + 1] = fmaf(ds[f][1], b.x, acc[j + 1]);
+            acc[j + 2] = fmaf(ds[f][0], b.x, acc[j + 2]); acc[j + 2] = fmaf(ds[f][1], b.y, acc[j + 2]);
+          }
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int f = 0; f < T; ++f) {
+          const int tap = f - t + 2;
+          if (tap < 0 || tap > 4) continue;
+          dwt_acc[tap] = fmaf(dy[t][0], s[f][0], dwt_acc[tap]);
+          dwt_acc[tap] = fmaf(dy[t][1], s[f][1], dwt_acc[tap]);
+        }
+    }
+    if (dperc) {
+      __syncthreads();                                          // ds of tile + halo complete
+      if (tid < NPP) {
+        const int ly = tid / (BTW / 2), x0 = 2 * (tid - ly * (BTW / 2));
+        const int h = h0 + ly, w = w0 + x0;
+        if (h < H && w < W) {
+          const long long HW = (long long)H * W, pix = (long long)h * W + w;
+#pragma unroll 1
+          for (int f = 1; f <= P; ++f) {
+            float g[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              // source pixel = output pixel - (kh - 1, kw - 1): halo row ly + 2 - kh, halo columns x0 + 2 - kw (+1)
+              const float* dp = dsp + ((f - 1) * NPIX + (ly + 2 - kh) * PW + x0) * STEM_DSLD;
+#pragma unroll 2
+              for (int q = 0; q < STEM_C / 4; ++q) {
+                float4 d[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = *reinterpret_cast<const float4*>(dp + k * STEM_DSLD + 4 * q);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                  for (int ci = 0; ci < 3; ++ci) {
+                    const float4 wv = *reinterpret_cast<const float4*>(s_wxy + (ci * 9 + kh * 3 + kw) * STEM_C + 4 * q);
+                    const float4 da = d[2 - kw], db = d[3 - kw];
+                    g[0][ci] = fmaf(da.x, wv.x, fmaf(da.y, wv.y, fmaf(da.z, wv.z, fmaf(da.w, wv.w, g[0][ci]))));
+                    g[1][ci] = fmaf(db.x, wv.x, fmaf(db.y, wv.y, fmaf(db.z, wv.z, fmaf(db.w, wv.w, g[1][ci]))));
+                  }
+              }
+            }
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              atomicAdd(dperc + (ci * P + (f - 1)) * HW + pix, g[0][ci]);
+              if (w + 1 < W) atomicAdd(dperc + (ci * P + (f - 1)) * HW + pix + 1, g[1][ci]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // flush: slots -> shared memory -> global
+#pragma unroll
+  for (int j = 0; j < 27; ++j) atomicAdd(&s_red[j * STEM_C + c], acc[j]);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) atomicAdd(&s_red[(27 + k) * STEM_C + c], dwt_acc[k]);
+  __syncthreads();
+  for (int i = tid; i < 27 * STEM_C; i += NT) { int k = i / STEM_C, cc = i - k * STEM_C; atomicAdd(dwxy + cc * 27 + k, s_red[i]); }
+  for (int i = tid; i < 5 * STEM_C; i += NT) { int k = i / STEM_C, cc = i - k * STEM_C; atomicAdd(dwt + cc * 5 + k, s_red[(27 + k) * STEM_C + cc]); }
+}
+
+template <int T, int BTW, int BTH, int NSLOT>
+static int launch_stem_bwd_pc(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
+                              const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
+                              cudaStream_t st) {
+  constexpr int P = T - 2, NPIX = (BTW + 2) * (BTH + 2);
+  const size_t smem = (size_t)(T * 3 * (BTH + 2) * (BTW + 4) + P * NPIX * STEM_DSLD + 27 * STEM_C + 32 * STEM_C) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(stem_bwd_pc_kernel<T, BTW, BTH, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return C3D_ERR_SMEM;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = ((W + BTW - 1) / BTW) * ((H + BTH - 1) / BTH) * B;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
+  const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
+  stem_bwd_pc_kernel<T, BTW, BTH, NSLOT><<<grid, NSLOT * STEM_C, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc,
+                                                                              B, H, W);
+  return c3d_check_last(cudaGetLastError());
+}
+
 // Tile = 16 x 8 pixels (73 KB of shared memory at T = 3: two CTAs per SM); C3D_STEM_BWD_TILE=32 selects the
 // 32 x 8 tile (133 KB, one CTA per SM) the kernel was first written for.
 template <int T>
 static int launch_stem_bwd(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
                            const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
                            cudaStream_t st) {
+  // C3D_STEM_BWD=0: the quad-per-thread kernel above (round 1; kept as a second implementation for the tests)
+  const char* m = getenv("C3D_STEM_BWD");
+  if (!m || atoi(m) != 0) {
+    if constexpr (T <= 4) return launch_stem_bwd_pc<T, 32, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
+    else return launch_stem_bwd_pc<T, 16, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
+  }
   const char* v = getenv("C3D_STEM_BWD_TILE");
   if (v && atoi(v) == 32)
     return launch_stem_bwd_tile<T, 32, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);

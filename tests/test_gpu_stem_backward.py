@@ -1,0 +1,65 @@
+"""Stem backward (c3d_stem_bwd: BN backward on the fly, temporal / spatial weight gradients, gradient of the shared
+perception frames) against torch autograd over the fp64 oracle, for both kernels behind the entry point
+(C3D_STEM_BWD=1: channel x pixel-pair kernel, the default; 0: the quad-per-thread kernel of round 1).
+Autograd of model/x3d.py:70-99 + the frame assembly of model/trainer.py:154-162."""
+import os
+
+import pytest
+import torch
+
+from oracle import change3d_oracle as O
+from tests.gpu_util import check
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _reference(sd, pre, post, perc, wgt, dtype):
+    osd = O.clone_sd({k: v for k, v in sd.items() if k.startswith("blocks.0.")}, dtype=dtype, requires_grad=True)
+    pr = perc.detach().clone().to(dtype).requires_grad_(True)
+    B = pre.shape[0]
+    x = torch.cat([pre.to(dtype).unsqueeze(2), pr.expand(B, -1, -1, -1, -1), post.to(dtype).unsqueeze(2)], dim=2)
+    out = O.stem(osd, x, True)
+    (out * wgt.to(dtype)).sum().backward()
+    return out.detach(), pr.grad, osd
+
+
+# odd widths / heights: partial tiles, pixel pairs cut by the image border, tiles in all corners
+@pytest.mark.parametrize("P,H,W,B", [(1, 20, 36, 2), (1, 19, 37, 3), (2, 24, 41, 2), (3, 17, 33, 2), (1, 64, 96, 2)])
+@pytest.mark.parametrize("impl", ["1", "0"])
+def test_stem_backward(P, H, W, B, impl):
+    from change3d_b200 import engine
+    from change3d_b200.model.x3d import create_x3d
+    sd = O.synth_state_dict(O.x3d_schema(), 11)
+    net = create_x3d(input_clip_length=3, depth_factor=5.0)
+    net.load_state_dict(sd, strict=True)
+    stem = net.blocks[0].to(DEV).train()
+    g = torch.Generator().manual_seed(100 * P + W)
+    pre, post = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+    perc = torch.randn(1, 3, P, H, W, generator=g)
+    T = P + 2
+    wgt = torch.randn(B, 24, T, H, W, generator=g)
+    out64, dperc64, g64 = _reference(sd, pre, post, perc, wgt, torch.float64)
+
+    hw = H * W
+    pre_d, post_d, perc_d = pre.to(DEV).contiguous(), post.to(DEV).contiguous(), perc.to(DEV).contiguous()
+    frames = [(pre_d, 3 * hw, hw)] + [(perc_d[0, :, f], 0, P * hw) for f in range(P)] + [(post_d, 3 * hw, hw)]
+    old = os.environ.get("C3D_STEM_BWD")
+    os.environ["C3D_STEM_BWD"] = impl
+    try:
+        out, (y, bnp, outs) = engine.stem_forward(stem, frames, B, H, W, True, True)
+        gd = wgt.permute(0, 2, 3, 4, 1).contiguous().to(DEV)                 # (B, T, H, W, 24)
+        dperc, dwxy, dwt, dgamma, dbeta = engine.stem_backward(stem, frames, y, bnp, outs, gd, P)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("C3D_STEM_BWD", None)
+        else:
+            os.environ["C3D_STEM_BWD"] = old
+    tag = f"stem_bwd impl{impl} P{P} {H}x{W}"
+    check(tag + " forward", out.permute(0, 4, 1, 2, 3), out64, 5e-6)
+    check(tag + " dperception", dperc, dperc64, 2e-5)
+    check(tag + " dw spatial", dwxy, g64["blocks.0.conv.conv_t.weight"].grad, 2e-5)
+    check(tag + " dw temporal", dwt, g64["blocks.0.conv.conv_xy.weight"].grad, 2e-5)
+    check(tag + " dgamma", dgamma, g64["blocks.0.norm.weight"].grad, 2e-5)
+    check(tag + " dbeta", dbeta, g64["blocks.0.norm.bias"].grad, 2e-5)
