@@ -75,7 +75,7 @@ SIGNATURES = {
     "c3d_convt_col2im": [_fp, _fp, _ll, _fp, _fp, _i, _i, _i, _i, _fp],
     "c3d_convt_im2col": [_fp, _fp, _i, _i, _i, _i, _fp],
     "c3d_stem_bwd": [C.POINTER(_fp), C.POINTER(_ll), C.POINTER(_ll), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
-                     _i, _i, _i, _i, _fp],
+                     _i, _i, _i, _i, _i, _fp],
     "c3d_dec_head_bwd": [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _fp],
     "c3d_adam_step": [_fp, _fp, _fp, _fp, _ll, _f, _f, _f, _f, _f, _i, _f, _f, _fp],
     "c3d_bce_dice_fwd": [_fp, _fp, _ll, _fp, _fp, _fp, _fp],

@@ -265,13 +265,14 @@ __global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __r
                                                                 float* __restrict__ dX, float* __restrict__ dW, int B, int H,
                                                                 int W, int is_sigmoid) {
   constexpr int C = 24, NQ = 6, PW = 34, PH = 10, NPIX = PW * PH;
+  constexpr int XPW = 35;   // odd row stride of the input tile: the 8 rows of a quarter warp fall into 8 different bank groups
   constexpr int NI = NCLS * NQ;                                // (class, quad) owners
   constexpr int TP = (256 / NI) > 32 ? 32 : (256 / NI);        // threads per owner; a tile has 32 segments of 8 pixels
   extern __shared__ __align__(16) float sm[];
   float* ws = sm;                        // [9][NCLS][24]
   float* red = ws + 9 * NCLS * C;        // [NCLS][24][9] weight-gradient reduction (end of the launch)
   float* dl = red + 9 * NCLS * C;        // [NCLS][NPIX]
-  float* xs = dl + ((NCLS * NPIX + 3) & ~3);   // [NPIX][HEAD_XLD]
+  float* xs = dl + ((NCLS * NPIX + 3) & ~3);   // [PH][XPW][HEAD_XLD]
   const int tid = threadIdx.x;
   for (int i = tid; i < 9 * NCLS * C; i += 256) {
     const int c = i % C, k = (i / C) % NCLS, tap = i / (C * NCLS);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __r
       const int h = h0 - 1 + y, ww = w0 - 1 + x;
       float4 v = f4zero();
       if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
-      *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v;
+      *reinterpret_cast<float4*>(xs + (y * XPW + x) * HEAD_XLD + 4 * q) = v;
     }
     __syncthreads();
     {  // dgrad: one thread per interior pixel; dX[i] = sum_{k,tap} w[k][.][tap] * dlogit[i - off(tap)][k]
@@ -340,19 +341,19 @@ __global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __r
     }
     if (wg_active) {  // dW[k][ci][tap] += sum_o dlogit[o][k] * X[o + off(tap)][ci]
       for (int seg = sub; seg < 32; seg += TP) {
-        const int row = seg >> 2, xs0 = (seg & 3) * 8;
-        const float* xb = xs + (row * PW + xs0) * HEAD_XLD + 4 * wq;       // halo (row + kh, xs0 + i + kw)
+        const int row = seg & 7, xs0 = (seg >> 3) * 8;              // lanes 0..7: rows 0..7 of one column block
+        const float* xb = xs + (row * XPW + xs0) * HEAD_XLD + 4 * wq;       // halo (row + kh, xs0 + i + kw)
         const float* db = dl + wk * NPIX + (row + 1) * PW + xs0 + 1;
         float4 win[3][3];                                                     // [column mod 3][kh]
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) win[j][kh] = *reinterpret_cast<const float4*>(xb + (kh * PW + j) * HEAD_XLD);
+          for (int kh = 0; kh < 3; ++kh) win[j][kh] = *reinterpret_cast<const float4*>(xb + (kh * XPW + j) * HEAD_XLD);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
-            win[(i + 2) % 3][kh] = *reinterpret_cast<const float4*>(xb + (kh * PW + i + 2) * HEAD_XLD);
+            win[(i + 2) % 3][kh] = *reinterpret_cast<const float4*>(xb + (kh * XPW + i + 2) * HEAD_XLD);
           const float d = db[i];
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __r
 template <int NCLS>
 static int launch_head_bwd24(const float* dpred, const float* pred, const float* X, const float* w, float* dX, float* dW,
                              int B, int H, int W, int is_sigmoid, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * 9 * NCLS * 24 + ((NCLS * 340 + 3) & ~3) + 340 * HEAD_XLD) * sizeof(float);
+  const size_t smem = (size_t)(2 * 9 * NCLS * 24 + ((NCLS * 340 + 3) & ~3) + 350 * HEAD_XLD) * sizeof(float);
   if (cudaFuncSetAttribute(dec_head_bwd24_kernel<NCLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return C3D_ERR_SMEM;
   int dev = 0, sms = 148;

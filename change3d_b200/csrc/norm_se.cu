@@ -230,16 +230,19 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
   if (tid < rpb * q4) {
     const int q = tid % q4, rl = tid / q4, c = 4 * q;
     const float4 mc = ldg4(bnp_c + c), rc = ldg4(bnp_c + Cs + c);
+    float4 sc = f4zero(), bc = f4zero();
+    if (!out) { sc = ldg4(bnp_c + 2 * Cs + c); bc = ldg4(bnp_c + 3 * Cs + c); }
     float4 m1 = f4zero(), r1 = f4zero();
     if (y1) { m1 = ldg4(bnp_1 + c); r1 = ldg4(bnp_1 + Cs + c); }
     float4 s = f4zero(), tc = f4zero(), t1 = f4zero();
     for (long long row = (long long)blockIdx.x * rpb + rl; row < M; row += (long long)gridDim.x * rpb) {
       const long long off = row * Cs + c;
       float4 d = ldg4(dOut + off);
-      const float4 o = ldg4(out + off);
-      d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
-      st4(d_pre + off, d);
       const float4 y = ldg4(yc + off);
+      // out = NULL: out == relu(bn_c(y_c)) (no shortcut), the mask comes from the forward's expression on y_c
+      const float4 o = out ? ldg4(out + off) : f4bn(y, mc, sc, bc);
+      d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+      if (d_pre) st4(d_pre + off, d);
       s = f4add(s, d);
       tc.x = fmaf(d.x, (y.x - mc.x) * rc.x, tc.x); tc.y = fmaf(d.y, (y.y - mc.y) * rc.y, tc.y);
       tc.z = fmaf(d.z, (y.z - mc.z) * rc.z, tc.z); tc.w = fmaf(d.w, (y.w - mc.w) * rc.w, tc.w);
@@ -270,8 +273,9 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
 extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const float* y_c, const float* bnp_c,
                                   const float* y_1, const float* bnp_1, float* d_pre, double* stats_c, double* stats_1,
                                   long long M, int Cs, void* stream_) {
-  if (!dOut || !out || !y_c || !bnp_c || !d_pre || !stats_c || M <= 0 || Cs <= 0 || (Cs & 3) || Cs > 1024) return C3D_ERR_ARG;
+  if (!dOut || !y_c || !bnp_c || !stats_c || M <= 0 || Cs <= 0 || (Cs & 3) || Cs > 1024) return C3D_ERR_ARG;
   if (y_1 && (!bnp_1 || !stats_1)) return C3D_ERR_ARG;
+  if (!out && y_1) return C3D_ERR_ARG;      // the recomputed mask is only valid without a shortcut
   const int rpb = 256 / (Cs >> 2);
   long long blocks = (M + rpb - 1) / rpb;
   if (blocks > 148 * 8) blocks = 148 * 8;

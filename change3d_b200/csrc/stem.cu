@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
                                                        const float* __restrict__ coef, const float* __restrict__ wxy,
                                                        const float* __restrict__ wt, float* __restrict__ dwxy,
                                                        float* __restrict__ dwt, float* __restrict__ dperc, int B, int H,
-                                                       int W) {
+                                                       int W, int relu_mask) {
   constexpr int P = T - 2;
   constexpr int PW = BTW + 2, PH = BTH + 2, NPIX = PW * PH;
   extern __shared__ __align__(16) float sm[];
@@ -325,7 +325,12 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
 #pragma unroll
           for (int t = 0; t < T; ++t) {
             const long long off = ((((long long)n * T + t) * H + h) * W + w) * STEM_C + ca;
-            const float4 d = ldg4(dpre + off), yv = ldg4(ys + off);
+            float4 d = ldg4(dpre + off);
+            const float4 yv = ldg4(ys + off);
+            if (relu_mask) {   // mask out > 0 recomputed from y (f4bn, the forward's expression)
+              const float4 o = f4bn(yv, mean, scale, ldg4(bnp + 3 * STEM_C + ca));
+              d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+            }
             dy[t].x = scale.x * (d.x - c1.x - (yv.x - mean.x) * rstd.x * c2.x);
             dy[t].y = scale.y * (d.y - c1.y - (yv.y - mean.y) * rstd.y * c2.y);
             dy[t].z = scale.z * (d.z - c1.z - (yv.z - mean.z) * rstd.z * c2.z);
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const StemFrames fr, cons
 template <int T, int BTW, int BTH>
 static int launch_stem_bwd_tile(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
                                 const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
-                                cudaStream_t st) {
+                                int relu_mask, cudaStream_t st) {
   static_assert(BTW * BTH <= 256 && (BTW & (BTW - 1)) == 0, "one thread per interior pixel in the perception-frame pass");
   constexpr int NPIX = (BTW + 2) * (BTH + 2);
   const size_t smem = (size_t)(T * 3 * NPIX + T * NPIX * STEM_DSLD + 27 * STEM_C * 2 + 5 * STEM_C * 2) * sizeof(float);
@@ -460,7 +465,7 @@ static int launch_stem_bwd_tile(const StemFrames& fr, const float* dpre, const f
   int per_sm = (int)((220 * 1024) / (smem + 1024));          // co-resident CTAs hide each other's phase barriers
   per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;           // 127 registers x 256 threads: two CTAs per SM
   int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
-  stem_bwd_kernel<T, BTW, BTH><<<grid, 256, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W);
+  stem_bwd_kernel<T, BTW, BTH><<<grid, 256, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, relu_mask);
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(NSLOT * STEM_C, 2)
 stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const float* __restrict__ ys,
                    const float* __restrict__ bnp, const float* __restrict__ coef, const float* __restrict__ wxy,
                    const float* __restrict__ wt, float* __restrict__ dwxy, float* __restrict__ dwt,
-                   float* __restrict__ dperc, int B, int H, int W) {
+                   float* __restrict__ dperc, int B, int H, int W, int relu_mask) {
   constexpr int P = T - 2;
   constexpr int NT = NSLOT * STEM_C;
   constexpr int PW = BTW + 2, PH = BTH + 2, NPIX = PW * PH;
@@ -507,6 +512,10 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
   for (int k = 0; k < 5; ++k) { wtr[k] = __ldg(wt + c * 5 + k); dwt_acc[k] = 0.f; }
   const float mean = __ldg(bnp + c), rstd = __ldg(bnp + STEM_C + c), scale = __ldg(bnp + 2 * STEM_C + c);
   const float c1 = __ldg(coef + c), c2 = __ldg(coef + STEM_C + c);
+  // relu_mask: `dpre` is the gradient w.r.t. the stem's ReLU output; the mask out > 0 is recomputed from y with the
+  // forward's own expression (f4bn in c3d_common.cuh), so the masked gradient is never written to memory.
+  const float beta = __ldg(bnp + 3 * STEM_C + c);
+  const float bT = -scale * rstd * c2, bC = -scale * c1;
   const long long fstride = (long long)H * W * STEM_C;          // one frame of d_pre / y
 
   const int tiles_x = (W + BTW - 1) / BTW, tiles_y = (H + BTH - 1) / BTH;
@@ -518,6 +527,29 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
     const float* dbase = dpre + (long long)n * T * fstride + c;
     const float* ybase = ys + (long long)n * T * fstride + c;
     __syncthreads();                                            // previous tile's perception pass is done
+    // BN backward of one element (+ the ReLU mask recomputed with the forward's expression when relu_mask):
+    // scale * (d - c1 - (y - mean) * rstd * c2) = bA * d + bT * (y - mean) + bC
+    auto bn_bwd = [&](float d, float yv) -> float {
+      const float t = yv - mean;
+      if (relu_mask && !(fmaf(t, scale, beta) > 0.f)) d = 0.f;
+      return fmaf(scale, d, fmaf(bT, t, bC));
+    };
+    float nd[T][2], ny[T][2];                                   // d_pre / y of the NEXT pixel pair (software prefetch)
+    auto fetch = [&](int pp) {
+      const int ly = pp / (BTW / 2), x0 = 2 * (pp - ly * (BTW / 2));
+      const int h = h0 + ly, w = w0 + x0;
+      const bool v0 = (h < H && w < W), v1 = (h < H && w + 1 < W);
+      const long long off = ((long long)h * W + w) * STEM_C;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        nd[t][0] = v0 ? __ldg(dbase + t * fstride + off) : 0.f;
+        ny[t][0] = v0 ? __ldg(ybase + t * fstride + off) : 0.f;
+        nd[t][1] = v1 ? __ldg(dbase + t * fstride + off + STEM_C) : 0.f;
+        ny[t][1] = v1 ? __ldg(ybase + t * fstride + off + STEM_C) : 0.f;
+      }
+    };
+    constexpr bool PREF = (T <= 4);                             // T = 5: the 20 prefetch registers would spill
+    if (PREF && slot < NPP) fetch(slot);                        // in flight across the patch fill and the halo ring
 #pragma unroll
     for (int f = 0; f < T; ++f) {                               // static f: the frame table stays in the parameter bank
       const float* fp = fr.p[f] + n * fr.sn[f];
@@ -543,8 +575,7 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
           const long long off = ((long long)h * W + w) * STEM_C;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const float d = __ldg(dbase + t * fstride + off), yv = __ldg(ybase + t * fstride + off);
-            dy[t] = scale * (d - c1 - (yv - mean) * rstd * c2);
+            dy[t] = bn_bwd(__ldg(dbase + t * fstride + off), __ldg(ybase + t * fstride + off));
           }
         } else {
 #pragma unroll
@@ -568,16 +599,14 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
       const int ly = pp / (BTW / 2), x0 = 2 * (pp - ly * (BTW / 2));
       const int h = h0 + ly, w = w0 + x0;
       const bool v0 = (h < H && w < W), v1 = (h < H && w + 1 < W);
-      const long long off = ((long long)h * W + w) * STEM_C;
       float dy[T][2], ds[T][2], s[T][2];
+      if (!PREF) fetch(pp);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        float d0 = 0.f, y0 = 0.f, d1 = 0.f, y1 = 0.f;
-        if (v0) { d0 = __ldg(dbase + t * fstride + off); y0 = __ldg(ybase + t * fstride + off); }
-        if (v1) { d1 = __ldg(dbase + t * fstride + off + STEM_C); y1 = __ldg(ybase + t * fstride + off + STEM_C); }
-        dy[t][0] = v0 ? scale * (d0 - c1 - (y0 - mean) * rstd * c2) : 0.f;
-        dy[t][1] = v1 ? scale * (d1 - c1 - (y1 - mean) * rstd * c2) : 0.f;
+        dy[t][0] = v0 ? bn_bwd(nd[t][0], ny[t][0]) : 0.f;
+        dy[t][1] = v1 ? bn_bwd(nd[t][1], ny[t][1]) : 0.f;
       }
+      if (PREF && pp + NSLOT < NPP) fetch(pp + NSLOT);          // next pair's loads fly during this pair's 360 FMA
 #pragma unroll
       for (int f = 0; f < T; ++f) {
         float o0 = 0.f, o1 = 0.f;
@@ -675,7 +704,7 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
 template <int T, int BTW, int BTH, int NSLOT>
 static int launch_stem_bwd_pc(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
                               const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
-                              cudaStream_t st) {
+                              int relu_mask, cudaStream_t st) {
   constexpr int P = T - 2, NPIX = (BTW + 2) * (BTH + 2);
   const size_t smem = (size_t)(T * 3 * (BTH + 2) * (BTW + 4) + P * NPIX * STEM_DSLD + 27 * STEM_C + 32 * STEM_C) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(stem_bwd_pc_kernel<T, BTW, BTH, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -688,7 +717,7 @@ static int launch_stem_bwd_pc(const StemFrames& fr, const float* dpre, const flo
   per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
   const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
   stem_bwd_pc_kernel<T, BTW, BTH, NSLOT><<<grid, NSLOT * STEM_C, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc,
-                                                                              B, H, W);
+                                                                              B, H, W, relu_mask);
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -697,31 +726,31 @@ static int launch_stem_bwd_pc(const StemFrames& fr, const float* dpre, const flo
 template <int T>
 static int launch_stem_bwd(const StemFrames& fr, const float* dpre, const float* ys, const float* bnp, const float* coef,
                            const float* wxy, const float* wt, float* dwxy, float* dwt, float* dperc, int B, int H, int W,
-                           cudaStream_t st) {
+                           int relu_mask, cudaStream_t st) {
   // C3D_STEM_BWD=0: the quad-per-thread kernel above (round 1; kept as a second implementation for the tests)
   const char* m = getenv("C3D_STEM_BWD");
   if (!m || atoi(m) != 0) {
-    if constexpr (T <= 4) return launch_stem_bwd_pc<T, 32, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
-    else return launch_stem_bwd_pc<T, 16, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
+    if constexpr (T <= 4) return launch_stem_bwd_pc<T, 32, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, relu_mask, st);
+    else return launch_stem_bwd_pc<T, 16, 8, 10>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, relu_mask, st);
   }
   const char* v = getenv("C3D_STEM_BWD_TILE");
   if (v && atoi(v) == 32)
-    return launch_stem_bwd_tile<T, 32, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
-  return launch_stem_bwd_tile<T, 16, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, st);
+    return launch_stem_bwd_tile<T, 32, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, relu_mask, st);
+  return launch_stem_bwd_tile<T, 16, 8>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc, B, H, W, relu_mask, st);
 }
 
 extern "C" int c3d_stem_bwd(const float* const* frame_ptr, const long long* stride_n, const long long* stride_c,
                             const float* d_pre, const float* y_raw, const float* bnp, const float* coef,
                             const float* w_xy, const float* w_t, float* dw_xy, float* dw_t, float* dperception, int B,
-                            int T, int H, int W, void* stream_) {
+                            int T, int H, int W, int relu_mask, void* stream_) {
   if (!d_pre || !y_raw || !bnp || !coef || !w_xy || !w_t || !dw_xy || !dw_t || B <= 0 || H <= 0 || W <= 0) return C3D_ERR_ARG;
   StemFrames fr;
   if (int e = stem_frames(fr, frame_ptr, stride_n, stride_c, T)) return e;
   cudaStream_t st = (cudaStream_t)stream_;
   switch (T) {
-    case 3: return launch_stem_bwd<3>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, st);
-    case 4: return launch_stem_bwd<4>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, st);
-    case 5: return launch_stem_bwd<5>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, st);
+    case 3: return launch_stem_bwd<3>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, relu_mask, st);
+    case 4: return launch_stem_bwd<4>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, relu_mask, st);
+    case 5: return launch_stem_bwd<5>(fr, d_pre, y_raw, bnp, coef, w_xy, w_t, dw_xy, dw_t, dperception, B, H, W, relu_mask, st);
     default: return C3D_ERR_ARG;
   }
 }

@@ -212,11 +212,13 @@ def dec_head_fwd(X: torch.Tensor, w: torch.Tensor, apply_sigmoid: bool) -> torch
 # ---------------------------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------------------------
-def relu_bwd_stats(dOut, out, y_c, bnp_c, y_1, bnp_1, stats_c, stats_1) -> torch.Tensor:
+def relu_bwd_stats(dOut, out, y_c, bnp_c, y_1, bnp_1, stats_c, stats_1, store: bool = True):
+    """out=None: the ReLU mask is recomputed from y_c / bnp_c (no shortcut).  store=False: statistics only (returns None)."""
     Cs = dOut.shape[-1]
     M = dOut.numel() // Cs
-    d_pre = torch.empty_like(dOut)
-    with _Timed("relu_bwd_stats", 4 * M * Cs * (5 if y_1 is not None else 4)):
+    d_pre = torch.empty_like(dOut) if store else None
+    nt = 2 + (1 if out is not None else 0) + (1 if store else 0) + (1 if y_1 is not None else 0)
+    with _Timed("relu_bwd_stats", 4 * M * Cs * nt):
         L.check(L.load().c3d_relu_bwd_stats(_ptr(dOut), _ptr(out), _ptr(y_c), _ptr(bnp_c), _ptr(y_1), _ptr(bnp_1),
                                             _ptr(d_pre), _ptr(stats_c), _ptr(stats_1), M, Cs, _stream()),
                 "c3d_relu_bwd_stats")
@@ -280,7 +282,8 @@ def convt_im2col(d_out: torch.Tensor, V: torch.Tensor, B: int, h: int, w: int, c
         L.check(L.load().c3d_convt_im2col(_ptr(d_out), _ptr(V), B, h, w, cout, _stream()), "c3d_convt_im2col")
 
 
-def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc) -> None:
+def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc, relu_mask: bool = False) -> None:
+    """relu_mask: `d_pre` is the gradient w.r.t. the ReLU output; the kernel recomputes the mask from y / bnp."""
     T = len(frames)
     B, _, H, W, _ = y.shape
     ptrs = (C.c_void_p * T)(*[f[0].data_ptr() for f in frames])
@@ -288,7 +291,7 @@ def stem_bwd(frames, d_pre, y, bnp, coef, w_xy, w_t, dwxy, dwt, dperc) -> None:
     sc = (C.c_longlong * T)(*[f[2] for f in frames])
     with _Timed("stem_bwd", 4 * (2 * y.numel() + B * T * 3 * H * W)):
       L.check(L.load().c3d_stem_bwd(ptrs, sn, sc, _ptr(d_pre), _ptr(y), _ptr(bnp), _ptr(coef), _ptr(w_xy), _ptr(w_t),
-                                  _ptr(dwxy), _ptr(dwt), _ptr(dperc), B, T, H, W, _stream()), "c3d_stem_bwd")
+                                  _ptr(dwxy), _ptr(dwt), _ptr(dperc), B, T, H, W, 1 if relu_mask else 0, _stream()), "c3d_stem_bwd")
 
 
 def dec_head_bwd(dpred, pred, X, w, is_sigmoid: bool, dW) -> torch.Tensor:

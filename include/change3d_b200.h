@@ -150,7 +150,9 @@ int c3d_dec_head_fwd(const float* X, const float* w, float* Y, int B, int H, int
 
 /* ReLU backward of a ResBlock / stem output fused with the BN backward reductions of the layer(s) below:
  * d_pre = dOut * (out > 0); stats_c[2][Cs] += (sum d_pre, sum d_pre*yhat_c); when the shortcut is normalised
- * (branch1_norm, model/x3d.py:296-298,312) stats_1 likewise with y_1 / bnp_1.  (autograd of model/x3d.py:326-327) */
+ * (branch1_norm, model/x3d.py:296-298,312) stats_1 likewise with y_1 / bnp_1.  (autograd of model/x3d.py:326-327)
+ * out = NULL: the mask is recomputed as (y_c - mean) * scale + beta > 0 from bnp_c (valid when `out` is exactly
+ * relu(bn_c(y_c)), i.e. no shortcut: the stem).  d_pre = NULL: statistics only, nothing is stored. */
 int c3d_relu_bwd_stats(const float* dOut, const float* out, const float* y_c, const float* bnp_c, const float* y_1,
                        const float* bnp_1, float* d_pre, double* stats_c, double* stats_1, long long M, int Cs,
                        void* cuda_stream);
@@ -180,13 +182,17 @@ int c3d_dw_conv_bwd(float* du, const float* y_b, const float* bnp_b, const float
 int c3d_colsum(const float* X, long long M, int Cs, float* out, void* cuda_stream);
 
 /* Stem backward (autograd of model/x3d.py:70-99 and of the frame assembly model/trainer.py:154-162).
- * d_pre = gradient after the ReLU mask, y_raw = saved raw stem output, coef from c3d_bn_bwd_finalize.
+ * y_raw = saved raw stem output, bnp[4][24] from c3d_bn_finalize, coef from c3d_bn_bwd_finalize.
+ * relu_mask = 0: d_pre is the gradient AFTER the ReLU mask (d_pre of c3d_relu_bwd_stats).
+ * relu_mask = 1: d_pre is the gradient w.r.t. the stem's ReLU output; the mask out > 0 is recomputed from y_raw and
+ *                bnp with the forward's own expression, so the masked copy never exists in memory (pair it with
+ *                c3d_relu_bwd_stats(out = NULL, d_pre = NULL) for the statistics).
  * dw_xy[24][27], dw_t[24][5], dperception[3][P][H][W] are accumulated with fp32 atomics (caller zeroes);
  * dperception may be NULL. */
 int c3d_stem_bwd(const float* const* frame_ptr, const long long* stride_n, const long long* stride_c,
                  const float* d_pre, const float* y_raw, const float* bnp, const float* coef, const float* w_xy,
                  const float* w_t, float* dw_xy, float* dw_t, float* dperception, int B, int T, int H, int W,
-                 void* cuda_stream);
+                 int relu_mask, void* cuda_stream);
 
 /* Decoder head backward (autograd of model/change_decoder.py:76-79): dpred/pred NCHW, X/dX NHWC, dW[ncls][C][3][3]
  * accumulated with fp32 atomics (caller zeroes). */

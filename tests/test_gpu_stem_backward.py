@@ -1,6 +1,7 @@
 """Stem backward (c3d_stem_bwd: BN backward on the fly, temporal / spatial weight gradients, gradient of the shared
 perception frames) against torch autograd over the fp64 oracle, for both kernels behind the entry point
-(C3D_STEM_BWD=1: channel x pixel-pair kernel, the default; 0: the quad-per-thread kernel of round 1).
+(C3D_STEM_BWD=1: channel x pixel-pair kernel, the default; 0: the quad-per-thread kernel of round 1), with the ReLU
+mask recomputed inside the kernels (C3D_STEM_MASKED=1, default) or applied by c3d_relu_bwd_stats beforehand.
 Autograd of model/x3d.py:70-99 + the frame assembly of model/trainer.py:154-162."""
 import os
 
@@ -26,8 +27,8 @@ def _reference(sd, pre, post, perc, wgt, dtype):
 
 # odd widths / heights: partial tiles, pixel pairs cut by the image border, tiles in all corners
 @pytest.mark.parametrize("P,H,W,B", [(1, 20, 36, 2), (1, 19, 37, 3), (2, 24, 41, 2), (3, 17, 33, 2), (1, 64, 96, 2)])
-@pytest.mark.parametrize("impl", ["1", "0"])
-def test_stem_backward(P, H, W, B, impl):
+@pytest.mark.parametrize("impl,masked", [("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")])
+def test_stem_backward(P, H, W, B, impl, masked):
     from change3d_b200 import engine
     from change3d_b200.model.x3d import create_x3d
     sd = O.synth_state_dict(O.x3d_schema(), 11)
@@ -44,19 +45,21 @@ def test_stem_backward(P, H, W, B, impl):
     hw = H * W
     pre_d, post_d, perc_d = pre.to(DEV).contiguous(), post.to(DEV).contiguous(), perc.to(DEV).contiguous()
     frames = [(pre_d, 3 * hw, hw)] + [(perc_d[0, :, f], 0, P * hw) for f in range(P)] + [(post_d, 3 * hw, hw)]
-    old = os.environ.get("C3D_STEM_BWD")
-    os.environ["C3D_STEM_BWD"] = impl
+    old = {k: os.environ.get(k) for k in ("C3D_STEM_BWD", "C3D_STEM_MASKED")}
+    os.environ["C3D_STEM_BWD"] = impl          # 1: channel x pixel-pair kernel, 0: quad-per-thread kernel
+    os.environ["C3D_STEM_MASKED"] = masked     # 1: ReLU mask recomputed from y inside the kernels, 0: masked copy in memory
     try:
         out, (y, bnp, outs) = engine.stem_forward(stem, frames, B, H, W, True, True)
         gd = wgt.permute(0, 2, 3, 4, 1).contiguous().to(DEV)                 # (B, T, H, W, 24)
         dperc, dwxy, dwt, dgamma, dbeta = engine.stem_backward(stem, frames, y, bnp, outs, gd, P)
         torch.cuda.synchronize()
     finally:
-        if old is None:
-            os.environ.pop("C3D_STEM_BWD", None)
-        else:
-            os.environ["C3D_STEM_BWD"] = old
-    tag = f"stem_bwd impl{impl} P{P} {H}x{W}"
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    tag = f"stem_bwd impl{impl} masked{masked} P{P} {H}x{W}"
     check(tag + " forward", out.permute(0, 4, 1, 2, 3), out64, 5e-6)
     check(tag + " dperception", dperc, dperc64, 2e-5)
     check(tag + " dw spatial", dwxy, g64["blocks.0.conv.conv_t.weight"].grad, 2e-5)
