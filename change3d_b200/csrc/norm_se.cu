@@ -214,7 +214,8 @@ extern "C" int c3d_version(void) { return C3D_ABI_VERSION; }
 // d_pre = dOut * (out > 0)   [ResBlock / stem ReLU backward]
 // stats_c += (sum d_pre, sum d_pre * yhat_c)  and, for a normalised shortcut, stats_1 likewise.
 // Threads keep a fixed channel quad so the column sums stay in registers.
-__global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
+template <int U>
+__global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_stats_kernel(
     const float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ yc,
     const float* __restrict__ bnp_c, const float* __restrict__ y1, const float* __restrict__ bnp_1,
     float* __restrict__ d_pre, double* __restrict__ stats_c, double* __restrict__ stats_1, long long M, int Cs) {
@@ -235,22 +236,41 @@ __global__ void __launch_bounds__(256) relu_bwd_stats_kernel(
     float4 m1 = f4zero(), r1 = f4zero();
     if (y1) { m1 = ldg4(bnp_1 + c); r1 = ldg4(bnp_1 + Cs + c); }
     float4 s = f4zero(), tc = f4zero(), t1 = f4zero();
-    for (long long row = (long long)blockIdx.x * rpb + rl; row < M; row += (long long)gridDim.x * rpb) {
-      const long long off = row * Cs + c;
-      float4 d = ldg4(dOut + off);
-      const float4 y = ldg4(yc + off);
-      // out = NULL: out == relu(bn_c(y_c)) (no shortcut), the mask comes from the forward's expression on y_c
-      const float4 o = out ? ldg4(out + off) : f4bn(y, mc, sc, bc);
+    auto consume = [&](long long off, float4 d, const float4 y, const float4 o, const float4 z) {
       d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
       if (d_pre) st4(d_pre + off, d);
       s = f4add(s, d);
       tc.x = fmaf(d.x, (y.x - mc.x) * rc.x, tc.x); tc.y = fmaf(d.y, (y.y - mc.y) * rc.y, tc.y);
       tc.z = fmaf(d.z, (y.z - mc.z) * rc.z, tc.z); tc.w = fmaf(d.w, (y.w - mc.w) * rc.w, tc.w);
       if (y1) {
-        const float4 z = ldg4(y1 + off);
         t1.x = fmaf(d.x, (z.x - m1.x) * r1.x, t1.x); t1.y = fmaf(d.y, (z.y - m1.y) * r1.y, t1.y);
         t1.z = fmaf(d.z, (z.z - m1.z) * r1.z, t1.z); t1.w = fmaf(d.w, (z.w - m1.w) * r1.w, t1.w);
       }
+    };
+    // U rows per iteration: all of their loads are issued before the first is consumed (3-4 loads per row and warp in
+    // flight do not cover the DRAM latency at 64 warps per SM: 4.4 TB/s with U = 1)
+    const long long rstep = (long long)gridDim.x * rpb;
+    long long row = (long long)blockIdx.x * rpb + rl;
+    for (; row + (U - 1) * rstep < M; row += U * rstep) {
+      float4 d[U], y[U], o[U], z[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long off = (row + u * rstep) * Cs + c;
+        d[u] = ldg4(dOut + off);
+        y[u] = ldg4(yc + off);
+        o[u] = out ? ldg4(out + off) : f4zero();
+        z[u] = y1 ? ldg4(y1 + off) : f4zero();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        // out = NULL: out == relu(bn_c(y_c)) (no shortcut), the mask comes from the forward's expression on y_c
+        consume((row + u * rstep) * Cs + c, d[u], y[u], out ? o[u] : f4bn(y[u], mc, sc, bc), z[u]);
+      }
+    }
+    for (; row < M; row += rstep) {
+      const long long off = row * Cs + c;
+      const float4 y = ldg4(yc + off);
+      consume(off, ldg4(dOut + off), y, out ? ldg4(out + off) : f4bn(y, mc, sc, bc), y1 ? ldg4(y1 + off) : f4zero());
     }
     atomicAdd(&sm[c], s.x); atomicAdd(&sm[c + 1], s.y); atomicAdd(&sm[c + 2], s.z); atomicAdd(&sm[c + 3], s.w);
     atomicAdd(&sm[Cs + c], tc.x); atomicAdd(&sm[Cs + c + 1], tc.y); atomicAdd(&sm[Cs + c + 2], tc.z); atomicAdd(&sm[Cs + c + 3], tc.w);
@@ -279,8 +299,17 @@ extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const flo
   const int rpb = 256 / (Cs >> 2);
   long long blocks = (M + rpb - 1) / rpb;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  c3d_launch_pdl(relu_bwd_stats_kernel, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_, 
-      dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
+  static int unroll = -1;           // C3D_EW_UNROLL: rows per loop iteration of the streaming elementwise kernels (1, 2, 4)
+  if (unroll < 0) { const char* v = getenv("C3D_EW_UNROLL"); unroll = v ? atoi(v) : 2; }
+  if (unroll >= 4)
+    c3d_launch_pdl(relu_bwd_stats_kernel<4>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
+        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
+  else if (unroll >= 2)
+    c3d_launch_pdl(relu_bwd_stats_kernel<2>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
+        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
+  else
+    c3d_launch_pdl(relu_bwd_stats_kernel<1>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
+        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
   return c3d_check_last(cudaGetLastError());
 }
 

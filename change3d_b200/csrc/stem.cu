@@ -538,14 +538,17 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
     auto fetch = [&](int pp) {
       const int ly = pp / (BTW / 2), x0 = 2 * (pp - ly * (BTW / 2));
       const int h = h0 + ly, w = w0 + x0;
-      const bool v0 = (h < H && w < W), v1 = (h < H && w + 1 < W);
-      const long long off = ((long long)h * W + w) * STEM_C;
+      // unconditional loads from clamped (always valid) addresses: pixels outside the image are zeroed through
+      // v0 / v1 where dy is formed, so the loop carries no divergent branches
+      const int hc = h < H ? h : H - 1, wc = w < W ? w : W - 1;
+      const int o1 = (w + 1 < W) ? STEM_C : 0;
+      const long long off = ((long long)hc * W + wc) * STEM_C;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        nd[t][0] = v0 ? __ldg(dbase + t * fstride + off) : 0.f;
-        ny[t][0] = v0 ? __ldg(ybase + t * fstride + off) : 0.f;
-        nd[t][1] = v1 ? __ldg(dbase + t * fstride + off + STEM_C) : 0.f;
-        ny[t][1] = v1 ? __ldg(ybase + t * fstride + off + STEM_C) : 0.f;
+        nd[t][0] = __ldg(dbase + t * fstride + off);
+        ny[t][0] = __ldg(ybase + t * fstride + off);
+        nd[t][1] = __ldg(dbase + t * fstride + off + o1);
+        ny[t][1] = __ldg(ybase + t * fstride + off + o1);
       }
     };
     constexpr bool PREF = (T <= 4);                             // T = 5: the 20 prefetch registers would spill

@@ -409,11 +409,18 @@ def res_stage_backward(stage, saved: List[BlockSaved], g: torch.Tensor):
     return g, ga.returned()
 
 
-def enhance_backward(out: torch.Tensor, mid_pre: torch.Tensor, fc_w: torch.Tensor, P: int, g: torch.Tensor):
+def stem_masked() -> bool:
+    """C3D_STEM_MASKED=1 (default): the stem backward recomputes the ReLU mask from the raw stem output y instead of
+    reading the published (enhanced in place) activation, so no masked gradient copy and no restore of the mid frame."""
+    return os.environ.get("C3D_STEM_MASKED", "1") != "0"
+
+
+def enhance_backward(out: torch.Tensor, mid_pre: torch.Tensor, fc_w: torch.Tensor, P: int, g: torch.Tensor,
+                     restore: bool = True):
     """Backward of the in-place enhance (model/trainer.py:88-108).  `g` (N,T,H,W,C) is the gradient w.r.t. the
     enhanced tensor and is updated in place to the gradient w.r.t. the stage output (frames 0 and P+1 receive
     -/+ sign(x0-x1) * W^T (g_mid * relu')); finally the saved stage output gets its pre-enhance mid frame back
-    so the stage's own ReLU mask is exact.  Returns dL/d fc_w."""
+    so the stage's own ReLU mask is exact (`restore=False`: the caller's backward does not read `out`).  Returns dL/d fc_w."""
     N, T, H, W, Cc = g.shape
     mid = T // 2
     fs = T * H * W * Cc
@@ -429,7 +436,8 @@ def enhance_backward(out: torch.Tensor, mid_pre: torch.Tensor, fc_w: torch.Tenso
     direct = getattr(fc_w, "_c3d_grad_view", None)
     dfc = direct if direct is not None else torch.zeros_like(fc_w)
     ops.pw_wgrad(de, absd, M=M, dW=dfc, dw_sn=Cc, dw_sk=1, N=Cc, K=Cc)
-    out[:, mid].copy_(mid_pre)
+    if restore:
+        out[:, mid].copy_(mid_pre)
     return None if direct is not None else dfc
 
 
@@ -444,7 +452,7 @@ def stem_backward(stem, frames, y, bnp, out, g, P: int, want_dperc: bool = True)
     st = torch.zeros(48, dtype=torch.float64, device=dev)
     # C3D_STEM_MASKED=1 (default): the masked gradient is never materialised -- the statistics pass and the stem
     # backward both recompute out > 0 from y (2 x 604 MB less traffic at batch 32, 256 x 256)
-    masked = os.environ.get("C3D_STEM_MASKED", "1") != "0"
+    masked = stem_masked()
     if masked:
         ops.relu_bwd_stats(g, None, y, bnp, None, None, st, None, store=False)
         d_pre = g

@@ -54,7 +54,8 @@ class _StemEnhFn(torch.autograd.Function):
         out, saved = engine.stem_forward(stem, frames, B, H, W, stem.training, need)
         mid_pre = None
         if fc_w is not None:
-            mid_pre = engine.enhance_forward(out, fc_w, P, need)
+            # the pre-enhance mid frame is only kept to restore the published tensor for a backward that reads it
+            mid_pre = engine.enhance_forward(out, fc_w, P, need and not engine.stem_masked())
         ctx.stem, ctx.saved, ctx.frames, ctx.mid_pre, ctx.fc_w, ctx.P = stem, saved, frames, mid_pre, fc_w, P
         ctx.keep = (pre, post, percc)
         ctx.set_materialize_grads(False)
@@ -67,7 +68,7 @@ class _StemEnhFn(torch.autograd.Function):
         g = _merge_slice_grads(g, gs, out, ctx.P)
         dfc = None
         if ctx.fc_w is not None:
-            dfc = engine.enhance_backward(out, ctx.mid_pre, ctx.fc_w, ctx.P, g)
+            dfc = engine.enhance_backward(out, ctx.mid_pre, ctx.fc_w, ctx.P, g, restore=not engine.stem_masked())
         dperc, dwxy, dwt, dgamma, dbeta = engine.stem_backward(ctx.stem, ctx.frames, y, bnp, out, g, ctx.P)
         ctx.saved = None
         return None, None, dperc, None, dfc, None, None, None, dwxy, dwt, dgamma, dbeta

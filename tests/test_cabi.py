@@ -74,6 +74,10 @@ def test_bad_arguments_return_status_without_device(lib):
     assert lib.c3d_dw_conv_fwd(1, 1, 1, 1, None, 1, 7, 8, 8, 24, 24, 1, None) == 1      # T out of range
     assert lib.c3d_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.99, 1e-8, 0.0, 1, 1.0, 0.0, None) == 1
     assert lib.c3d_stem_fwd(None, None, None, None, None, None, None, 1, 3, 8, 8, None) == 1
+    assert lib.c3d_stem_bwd(None, None, None, None, None, None, None, None, None, None, None, None, 1, 3, 8, 8, 1, None) == 1
+    # ReLU mask recomputed from y_c (out = NULL) is only defined without a normalised shortcut
+    assert lib.c3d_relu_bwd_stats(1, None, 1, 1, 1, 1, None, 1, 1, 64, 24, None) == 1
+    assert lib.c3d_relu_bwd_stats(1, None, 1, 1, None, None, None, None, None, 64, 24, None) == 1     # no statistics buffer
     assert lib.c3d_attention_fwd(None, None) == 1
     ad = _lib.AttnDesc()
     ad.q = ad.k = ad.v = ad.o = 1
