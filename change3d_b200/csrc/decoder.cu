@@ -475,6 +475,45 @@ __global__ void __launch_bounds__(256) convt_im2col_kernel(const float* __restri
   }
 }
 
+// Same gather with 32-bit index arithmetic (total4 < 2^31), the quad count as a template parameter (division by a
+// constant) and U elements per iteration with their loads issued first: the generic kernel above spends its time on
+// three 64-bit divisions per 16 bytes (ncu: 66 % issue-active at 3.0 TB/s).
+template <int C4N, int U>
+__global__ void __launch_bounds__(256) convt_im2col32_kernel(const float* __restrict__ dout, float* __restrict__ V, unsigned h,
+                                                             unsigned w, unsigned total4) {
+  const unsigned OW = 2 * w, OH = 2 * h, cout = 4 * C4N;
+  const unsigned stride = gridDim.x * blockDim.x;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  auto src_of = [&](unsigned id, bool& ok) -> const float* {
+    const unsigned c = (id % C4N) * 4;
+    unsigned r = id / C4N;
+    const unsigned tap = r & 15u;
+    r >>= 4;
+    const unsigned i = r % w;
+    r /= w;
+    const unsigned j = r % h, b = r / h;
+    const int y = 2 * (int)j - 1 + (int)(tap >> 2), x = 2 * (int)i - 1 + (int)(tap & 3);
+    ok = y >= 0 && y < (int)OH && x >= 0 && x < (int)OW;
+    return dout + ((size_t)(b * OH + (unsigned)y) * OW + (unsigned)x) * cout + c;
+  };
+  for (; (unsigned long long)idx + (unsigned long long)(U - 1) * stride < total4; idx += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool ok;
+      const float* p = src_of(idx + u * stride, ok);
+      v[u] = ok ? ldg4(p) : f4zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) st4(V + (size_t)(idx + u * stride) * 4, v[u]);
+  }
+  for (; idx < total4; idx += stride) {
+    bool ok;
+    const float* p = src_of(idx, ok);
+    st4(V + (size_t)idx * 4, ok ? ldg4(p) : f4zero());
+  }
+}
+
 extern "C" int c3d_convt_col2im(const float* U, const float* skip, long long skip_img_stride, const float* bias, float* out,
                                 int B, int h, int w, int cout, void* stream_) {
   if (!U || !bias || !out || B <= 0 || h <= 0 || w <= 0 || cout <= 0 || (cout & 3)) return C3D_ERR_ARG;
@@ -490,6 +529,17 @@ extern "C" int c3d_convt_im2col(const float* dout, float* V, int B, int h, int w
   const long long total4 = (long long)B * h * w * 16 * (cout >> 2);
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
+  // all index products below 2^31: 32-bit kernel (the Change3D decoders: cout = 24 / 48 / 96 ... any multiple of 4 up to 96)
+  if (total4 < (1ll << 31) && (long long)B * 4 * h * w * cout < (1ll << 31) && head_fast_path()) {
+    const unsigned ub = (unsigned)blocks;
+    cudaStream_t st = (cudaStream_t)stream_;
+    switch (cout >> 2) {
+      case 6: convt_im2col32_kernel<6, 4><<<ub, 256, 0, st>>>(dout, V, (unsigned)h, (unsigned)w, (unsigned)total4); return c3d_check_last(cudaGetLastError());
+      case 12: convt_im2col32_kernel<12, 4><<<ub, 256, 0, st>>>(dout, V, (unsigned)h, (unsigned)w, (unsigned)total4); return c3d_check_last(cudaGetLastError());
+      case 24: convt_im2col32_kernel<24, 4><<<ub, 256, 0, st>>>(dout, V, (unsigned)h, (unsigned)w, (unsigned)total4); return c3d_check_last(cudaGetLastError());
+      default: break;
+    }
+  }
   convt_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(dout, V, h, w, cout, total4);
   return c3d_check_last(cudaGetLastError());
 }

@@ -170,6 +170,7 @@ extern "C" int c3d_bn_se_finalize(const double* stats, int N, long long count_pe
   return c3d_check_last(cudaGetLastError());
 }
 
+template <int U>
 __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restrict__ A, const float* __restrict__ bnpA,
                                                           const float* __restrict__ B, const float* __restrict__ bnpB,
                                                           float* __restrict__ Y, long long total4, int Cs) {
@@ -182,17 +183,53 @@ __global__ void __launch_bounds__(256) bn_add_relu_kernel(const float* __restric
   const unsigned stride = gridDim.x * blockDim.x;
   const int cstep = (int)(stride % (unsigned)q4) * 4;
   int c = (int)(i0 % q4) * 4;
-  for (long long i = i0; i < total4; i += stride) {
-    float4 v = f4bn(ldg4(A + i * 4), ldg4(bnpA + c), ldg4(bnpA + 2 * Cs + c), ldg4(bnpA + 3 * Cs + c));
+  auto one = [&](long long i, int cc, float4 a, float4 b) {
+    float4 v = f4bn(a, ldg4(bnpA + cc), ldg4(bnpA + 2 * Cs + cc), ldg4(bnpA + 3 * Cs + cc));
     if (B) {
-      float4 b = ldg4(B + i * 4);
-      if (bnpB) b = f4bn(b, ldg4(bnpB + c), ldg4(bnpB + 2 * Cs + c), ldg4(bnpB + 3 * Cs + c));
+      if (bnpB) b = f4bn(b, ldg4(bnpB + cc), ldg4(bnpB + 2 * Cs + cc), ldg4(bnpB + 3 * Cs + cc));
       v = f4add(v, b);
     }
     st4(Y + i * 4, f4relu(v));
+  };
+  long long i = i0;
+  // U elements per iteration, their streaming loads issued before the first is consumed
+  for (; i + (long long)(U - 1) * stride < total4; i += (long long)U * stride) {
+    float4 a[U], b[U];
+    int cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long iu = i + (long long)u * stride;
+      a[u] = ldg4(A + iu * 4);
+      b[u] = B ? ldg4(B + iu * 4) : f4zero();
+      cc[u] = c;
+      c += cstep;
+      if (c >= Cs) c -= Cs;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(i + (long long)u * stride, cc[u], a[u], b[u]);
+  }
+  for (; i < total4; i += stride) {
+    one(i, c, ldg4(A + i * 4), B ? ldg4(B + i * 4) : f4zero());
     c += cstep;
     if (c >= Cs) c -= Cs;
   }
+}
+
+// CTAs of `kernel` that fit the device at once: the streaming kernels below loop with a grid stride, so a grid of more
+// than one resident wave only adds a partially filled last wave
+template <typename K>
+static long long resident_ctas(K kernel, int threads, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return (long long)sms * per_sm;
+}
+
+static int ew_unroll() {             // C3D_EW_UNROLL: elements / rows per loop iteration of the streaming elementwise kernels
+  static int u = -1;
+  if (u < 0) { const char* v = getenv("C3D_EW_UNROLL"); u = v ? atoi(v) : 4; }
+  return u;
 }
 
 extern "C" int c3d_bn_add_relu(const float* A, const float* bnpA, const float* B, const float* bnpB, float* Y,
@@ -200,8 +237,13 @@ extern "C" int c3d_bn_add_relu(const float* A, const float* bnpA, const float* B
   if (!A || !bnpA || !Y || M <= 0 || Cs <= 0 || (Cs & 3)) return C3D_ERR_ARG;
   const long long total4 = M * (Cs >> 2);
   long long blocks = (total4 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  c3d_launch_pdl(bn_add_relu_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, A, bnpA, B, bnpB, Y, total4, Cs);
+  const int u = ew_unroll();
+#define BAR_LAUNCH(U_) do { const long long cap = resident_ctas(bn_add_relu_kernel<U_>, 256, 0); if (blocks > cap) blocks = cap; \
+    c3d_launch_pdl(bn_add_relu_kernel<U_>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream_, A, bnpA, B, bnpB, Y, total4, Cs); } while (0)
+  if (u >= 4) BAR_LAUNCH(4);
+  else if (u >= 2) BAR_LAUNCH(2);
+  else BAR_LAUNCH(1);
+#undef BAR_LAUNCH
   return c3d_check_last(cudaGetLastError());
 }
 
@@ -214,8 +256,10 @@ extern "C" int c3d_version(void) { return C3D_ABI_VERSION; }
 // d_pre = dOut * (out > 0)   [ResBlock / stem ReLU backward]
 // stats_c += (sum d_pre, sum d_pre * yhat_c)  and, for a normalised shortcut, stats_1 likewise.
 // Threads keep a fixed channel quad so the column sums stay in registers.
-template <int U>
-__global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_stats_kernel(
+// HAS1: normalised shortcut (y1 / bnp_1 / stats_1); MASKY: out == NULL, the mask is recomputed from y_c.  Both are template
+// parameters so that the common case (neither) keeps 12 registers per row in flight and three CTAs per SM at U = 4.
+template <int U, bool HAS1, bool MASKY>
+__global__ void __launch_bounds__(256, (U >= 4 && (HAS1 || MASKY)) ? 2 : U >= 2 ? 3 : 4) relu_bwd_stats_kernel(
     const float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ yc,
     const float* __restrict__ bnp_c, const float* __restrict__ y1, const float* __restrict__ bnp_1,
     float* __restrict__ d_pre, double* __restrict__ stats_c, double* __restrict__ stats_1, long long M, int Cs) {
@@ -232,9 +276,9 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_sta
     const int q = tid % q4, rl = tid / q4, c = 4 * q;
     const float4 mc = ldg4(bnp_c + c), rc = ldg4(bnp_c + Cs + c);
     float4 sc = f4zero(), bc = f4zero();
-    if (!out) { sc = ldg4(bnp_c + 2 * Cs + c); bc = ldg4(bnp_c + 3 * Cs + c); }
+    if (MASKY) { sc = ldg4(bnp_c + 2 * Cs + c); bc = ldg4(bnp_c + 3 * Cs + c); }
     float4 m1 = f4zero(), r1 = f4zero();
-    if (y1) { m1 = ldg4(bnp_1 + c); r1 = ldg4(bnp_1 + Cs + c); }
+    if (HAS1) { m1 = ldg4(bnp_1 + c); r1 = ldg4(bnp_1 + Cs + c); }
     float4 s = f4zero(), tc = f4zero(), t1 = f4zero();
     auto consume = [&](long long off, float4 d, const float4 y, const float4 o, const float4 z) {
       d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f; d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
@@ -242,7 +286,7 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_sta
       s = f4add(s, d);
       tc.x = fmaf(d.x, (y.x - mc.x) * rc.x, tc.x); tc.y = fmaf(d.y, (y.y - mc.y) * rc.y, tc.y);
       tc.z = fmaf(d.z, (y.z - mc.z) * rc.z, tc.z); tc.w = fmaf(d.w, (y.w - mc.w) * rc.w, tc.w);
-      if (y1) {
+      if (HAS1) {
         t1.x = fmaf(d.x, (z.x - m1.x) * r1.x, t1.x); t1.y = fmaf(d.y, (z.y - m1.y) * r1.y, t1.y);
         t1.z = fmaf(d.z, (z.z - m1.z) * r1.z, t1.z); t1.w = fmaf(d.w, (z.w - m1.w) * r1.w, t1.w);
       }
@@ -252,29 +296,29 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_sta
     const long long rstep = (long long)gridDim.x * rpb;
     long long row = (long long)blockIdx.x * rpb + rl;
     for (; row + (U - 1) * rstep < M; row += U * rstep) {
-      float4 d[U], y[U], o[U], z[U];
+      float4 d[U], y[U], o[MASKY ? 1 : U], z[HAS1 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long off = (row + u * rstep) * Cs + c;
         d[u] = ldg4(dOut + off);
         y[u] = ldg4(yc + off);
-        o[u] = out ? ldg4(out + off) : f4zero();
-        z[u] = y1 ? ldg4(y1 + off) : f4zero();
+        if (!MASKY) o[u] = ldg4(out + off);
+        if (HAS1) z[u] = ldg4(y1 + off);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        // out = NULL: out == relu(bn_c(y_c)) (no shortcut), the mask comes from the forward's expression on y_c
-        consume((row + u * rstep) * Cs + c, d[u], y[u], out ? o[u] : f4bn(y[u], mc, sc, bc), z[u]);
+        // MASKY: out == relu(bn_c(y_c)) (no shortcut), the mask comes from the forward's expression on y_c
+        consume((row + u * rstep) * Cs + c, d[u], y[u], MASKY ? f4bn(y[u], mc, sc, bc) : o[u], HAS1 ? z[u] : f4zero());
       }
     }
     for (; row < M; row += rstep) {
       const long long off = row * Cs + c;
       const float4 y = ldg4(yc + off);
-      consume(off, ldg4(dOut + off), y, out ? ldg4(out + off) : f4bn(y, mc, sc, bc), y1 ? ldg4(y1 + off) : f4zero());
+      consume(off, ldg4(dOut + off), y, MASKY ? f4bn(y, mc, sc, bc) : ldg4(out + off), HAS1 ? ldg4(y1 + off) : f4zero());
     }
     atomicAdd(&sm[c], s.x); atomicAdd(&sm[c + 1], s.y); atomicAdd(&sm[c + 2], s.z); atomicAdd(&sm[c + 3], s.w);
     atomicAdd(&sm[Cs + c], tc.x); atomicAdd(&sm[Cs + c + 1], tc.y); atomicAdd(&sm[Cs + c + 2], tc.z); atomicAdd(&sm[Cs + c + 3], tc.w);
-    if (y1) {
+    if (HAS1) {
       atomicAdd(&sm[2 * Cs + c], t1.x); atomicAdd(&sm[2 * Cs + c + 1], t1.y);
       atomicAdd(&sm[2 * Cs + c + 2], t1.z); atomicAdd(&sm[2 * Cs + c + 3], t1.w);
     }
@@ -283,7 +327,7 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : U == 2 ? 3 : 2) relu_bwd_sta
   for (int i = threadIdx.x; i < Cs; i += 256) {
     atomicAdd(stats_c + i, (double)sm[i]);
     atomicAdd(stats_c + Cs + i, (double)sm[Cs + i]);
-    if (y1) {
+    if (HAS1) {
       atomicAdd(stats_1 + i, (double)sm[i]);
       atomicAdd(stats_1 + Cs + i, (double)sm[2 * Cs + i]);
     }
@@ -299,17 +343,21 @@ extern "C" int c3d_relu_bwd_stats(const float* dOut, const float* out, const flo
   const int rpb = 256 / (Cs >> 2);
   long long blocks = (M + rpb - 1) / rpb;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  static int unroll = -1;           // C3D_EW_UNROLL: rows per loop iteration of the streaming elementwise kernels (1, 2, 4)
-  if (unroll < 0) { const char* v = getenv("C3D_EW_UNROLL"); unroll = v ? atoi(v) : 2; }
-  if (unroll >= 4)
-    c3d_launch_pdl(relu_bwd_stats_kernel<4>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
-        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
-  else if (unroll >= 2)
-    c3d_launch_pdl(relu_bwd_stats_kernel<2>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
-        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
-  else
-    c3d_launch_pdl(relu_bwd_stats_kernel<1>, dim3((unsigned)blocks), dim3(256), 3 * Cs * sizeof(float), (cudaStream_t)stream_,
-        dOut, out, y_c, bnp_c, y_1, bnp_1, d_pre, stats_c, stats_1, M, Cs);
+  const int unroll = ew_unroll();
+  const dim3 blk(256);
+  const size_t smem = 3 * Cs * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream_;
+#define RBS_LAUNCH(U_, H_, K_) do { const long long cap = resident_ctas(relu_bwd_stats_kernel<U_, H_, K_>, 256, smem);            \
+    if (blocks > cap) blocks = cap;                                                                                            \
+    c3d_launch_pdl(relu_bwd_stats_kernel<U_, H_, K_>, dim3((unsigned)blocks), blk, smem, st, dOut, out, y_c, bnp_c, y_1,         \
+                   bnp_1, d_pre, stats_c, stats_1, M, Cs); } while (0)
+#define RBS_PICK(U_) do { if (y_1) RBS_LAUNCH(U_, true, false); else if (!out) RBS_LAUNCH(U_, false, true); \
+                          else RBS_LAUNCH(U_, false, false); } while (0)
+  if (unroll >= 4) RBS_PICK(4);
+  else if (unroll >= 2) RBS_PICK(2);
+  else RBS_PICK(1);
+#undef RBS_PICK
+#undef RBS_LAUNCH
   return c3d_check_last(cudaGetLastError());
 }
 
