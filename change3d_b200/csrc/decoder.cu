@@ -76,12 +76,29 @@ __global__ void __launch_bounds__(256) dec_head_fwd24_kernel(const float* __rest
     const int c = i % C, k = (i / C) % NCLS, tap = i / (C * NCLS);
     ws[i] = __ldg(w + (k * C + c) * 9 + tap);
   }
-  for (int i = tid; i < NPIX * NQ; i += 256) {
-    const int p = i / NQ, q = i - p * NQ, y = p / PW, x = p - y * PW;
-    const int h = h0 - 1 + y, ww = w0 - 1 + x;
-    float4 v = f4zero();
-    if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
-    *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v;
+  // tile staging in batches of 4 quads per thread: loads (clamped, always valid addresses) first, then the stores
+  constexpr int XS_IT = (NPIX * NQ + 255) / 256;
+#pragma unroll
+  for (int k0 = 0; k0 < XS_IT; k0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + (k0 + u) * 256;
+      const int ic = (k0 + u < XS_IT && i < NPIX * NQ) ? i : 0;
+      const int p = ic / NQ, q = ic - p * NQ, y = p / PW, x = p - y * PW;
+      const int h = h0 - 1 + y, ww = w0 - 1 + x;
+      const int hc = h < 0 ? 0 : h >= H ? H - 1 : h, wc = ww < 0 ? 0 : ww >= W ? W - 1 : ww;
+      const float4 t = ldg4(X + (((long long)n * H + hc) * W + wc) * C + 4 * q);
+      v[u] = (hc == h && wc == ww) ? t : f4zero();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + (k0 + u) * 256;
+      if (k0 + u < XS_IT && i < NPIX * NQ) {
+        const int p = i / NQ, q = i - p * NQ;
+        *reinterpret_cast<float4*>(xs + p * HEAD_XLD + 4 * q) = v[u];
+      }
+    }
   }
   __syncthreads();
   const int lx = tid & 31, ly = tid >> 5;
@@ -302,12 +319,29 @@ __global__ void __launch_bounds__(256, 2) dec_head_bwd24_kernel(const float* __r
       }
       dl[i] = v;
     }
-    for (int i = tid; i < NPIX * NQ; i += 256) {
-      const int p = i / NQ, q = i - p * NQ, y = p / PW, x = p - y * PW;
-      const int h = h0 - 1 + y, ww = w0 - 1 + x;
-      float4 v = f4zero();
-      if (h >= 0 && h < H && ww >= 0 && ww < W) v = ldg4(X + (((long long)n * H + h) * W + ww) * C + 4 * q);
-      *reinterpret_cast<float4*>(xs + (y * XPW + x) * HEAD_XLD + 4 * q) = v;
+    // input tile in batches of 4 quads per thread: loads (clamped, always valid addresses) first, then the stores
+    constexpr int XS_IT = (NPIX * NQ + 255) / 256;
+#pragma unroll
+    for (int k0 = 0; k0 < XS_IT; k0 += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = tid + (k0 + u) * 256;
+        const int ic = (k0 + u < XS_IT && i < NPIX * NQ) ? i : 0;
+        const int p = ic / NQ, q = ic - p * NQ, y = p / PW, x = p - y * PW;
+        const int h = h0 - 1 + y, ww = w0 - 1 + x;
+        const int hc = h < 0 ? 0 : h >= H ? H - 1 : h, wc = ww < 0 ? 0 : ww >= W ? W - 1 : ww;
+        const float4 t = ldg4(X + (((long long)n * H + hc) * W + wc) * C + 4 * q);
+        v[u] = (hc == h && wc == ww) ? t : f4zero();
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = tid + (k0 + u) * 256;
+        if (k0 + u < XS_IT && i < NPIX * NQ) {
+          const int p = i / NQ, q = i - p * NQ, y = p / PW, x = p - y * PW;
+          *reinterpret_cast<float4*>(xs + (y * XPW + x) * HEAD_XLD + 4 * q) = v[u];
+        }
+      }
     }
     __syncthreads();
     {  // dgrad: one thread per interior pixel; dX[i] = sum_{k,tap} w[k][.][tap] * dlogit[i - off(tap)][k]

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemFrames fr, cons
 // 24 consecutive lanes store the 24 channels of a pixel (whole sectors); the BatchNorm sums stay in per-thread
 // registers (fp32 within a tile, fp64 across the tiles of a persistent CTA) and are reduced once per launch.
 template <int T, int NSLOT>
-__global__ void __launch_bounds__(NSLOT * STEM_C) stem_fwd_pc_kernel(const StemFrames fr, const float* __restrict__ wxy,
+__global__ void __launch_bounds__(NSLOT * STEM_C, T <= 4 ? 4 : 3) stem_fwd_pc_kernel(const StemFrames fr, const float* __restrict__ wxy,
                                                                       const float* __restrict__ wt, float* __restrict__ Y,
                                                                       double* __restrict__ stats, int B, int H, int W) {
   constexpr int NT = NSLOT * STEM_C;
@@ -131,17 +131,32 @@ __global__ void __launch_bounds__(NSLOT * STEM_C) stem_fwd_pc_kernel(const StemF
     const int trem = tile - n * tiles_x * tiles_y;
     const int h0 = (trem / tiles_x) * STEM_TH, w0 = (trem % tiles_x) * STEM_TW;
     __syncthreads();
+    // all loads of a frame's patch are issued (clamped, always valid addresses) before the first store
+    constexpr int FILL_IT = (3 * NPIX + NT - 1) / NT;
 #pragma unroll
     for (int f = 0; f < T; ++f) {
       const float* fp = fr.p[f] + n * fr.sn[f];
       const long long fsc = fr.sc[f];
-      for (int i = tid; i < 3 * NPIX; i += NT) {
-        const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+      float v[FILL_IT];
+#pragma unroll
+      for (int k = 0; k < FILL_IT; ++k) {
+        const int i = tid + k * NT;
+        const int ic = i < 3 * NPIX ? i : 0;
+        const int x = ic % PW, y = (ic / PW) % PH, ci = ic / NPIX;
         const int h = h0 - 1 + y, w = w0 - 1 + x;
-        float v = 0.f;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(fp + ci * fsc + (long long)h * W + w);
-        patch[((f * 3 + ci) * PH + y) * PWP + x] = v;
+        const int hc = h < 0 ? 0 : h >= H ? H - 1 : h, wc = w < 0 ? 0 : w >= W ? W - 1 : w;
+        const float t = __ldg(fp + ci * fsc + (long long)hc * W + wc);
+        v[k] = (hc == h && wc == w) ? t : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < FILL_IT; ++k) {
+        const int i = tid + k * NT;
+        if (i < 3 * NPIX) {
+          const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+          patch[((f * 3 + ci) * PH + y) * PWP + x] = v[k];
+        }
+      }
+      asm volatile("" ::: "memory");      // one frame's batch at a time: keeps FILL_IT values live, not T * FILL_IT
     }
     __syncthreads();
     float psum = 0.f, psq = 0.f;
@@ -553,47 +568,80 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
     };
     constexpr bool PREF = (T <= 4);                             // T = 5: the 20 prefetch registers would spill
     if (PREF && slot < NPP) fetch(slot);                        // in flight across the patch fill and the halo ring
+    // Patch fill and halo ring: the loads of a whole batch are issued (from clamped, always valid addresses) before the
+    // first value is used -- with one dependent load -> store chain per loop iteration this phase took 41 % of the
+    // kernel's time for 17 % of its instructions (ncu source view, profiles/r02_summary.md section 2.5).
+    constexpr int FILL_IT = (3 * NPIX + NT - 1) / NT;
 #pragma unroll
     for (int f = 0; f < T; ++f) {                               // static f: the frame table stays in the parameter bank
       const float* fp = fr.p[f] + n * fr.sn[f];
       const long long fsc = fr.sc[f];
-      for (int i = tid; i < 3 * NPIX; i += NT) {
-        const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+      float v[FILL_IT];
+#pragma unroll
+      for (int k = 0; k < FILL_IT; ++k) {
+        const int i = tid + k * NT;
+        const int ic = i < 3 * NPIX ? i : 0;
+        const int x = ic % PW, y = (ic / PW) % PH, ci = ic / NPIX;
         const int h = h0 - 1 + y, w = w0 - 1 + x;
-        float v = 0.f;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(fp + ci * fsc + (long long)h * W + w);
-        patch[((f * 3 + ci) * PH + y) * PWP + x] = v;
+        const int hc = h < 0 ? 0 : h >= H ? H - 1 : h, wc = w < 0 ? 0 : w >= W ? W - 1 : w;
+        const float t = __ldg(fp + ci * fsc + (long long)hc * W + wc);
+        v[k] = (hc == h && wc == w) ? t : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < FILL_IT; ++k) {
+        const int i = tid + k * NT;
+        if (i < 3 * NPIX) {
+          const int x = i % PW, y = (i / PW) % PH, ci = i / NPIX;
+          patch[((f * 3 + ci) * PH + y) * PWP + x] = v[k];
+        }
+      }
+      asm volatile("" ::: "memory");      // one frame's batch at a time: keeps FILL_IT values live, not T * FILL_IT
     }
     if (dperc) {
-      // halo ring: ds of the perception frames only
-      for (int hp = slot; hp < NHALO; hp += NSLOT) {
-        int y, x;
-        if (hp < PW) { y = 0; x = hp; }
-        else if (hp < 2 * PW) { y = PH - 1; x = hp - PW; }
-        else { const int r = hp - 2 * PW; y = 1 + (r >> 1); x = (r & 1) ? PW - 1 : 0; }
-        const int h = h0 - 1 + y, w = w0 - 1 + x;
-        float dy[T];
-        if (h >= 0 && h < H && w >= 0 && w < W) {
-          const long long off = ((long long)h * W + w) * STEM_C;
+      // halo ring: ds of the perception frames only, HB pixels per batch
+      constexpr int HB = 3;
+      constexpr int HALO_IT = (NHALO + NSLOT - 1) / NSLOT;
+#pragma unroll 1
+      for (int k0 = 0; k0 < HALO_IT; k0 += HB) {
+        float hd[HB][T], hy[HB][T];
+        int hpos[HB];
+        bool hin[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+          const int hp = slot + (k0 + u) * NSLOT;
+          const int hq = hp < NHALO ? hp : 0;
+          int y, x;
+          if (hq < PW) { y = 0; x = hq; }
+          else if (hq < 2 * PW) { y = PH - 1; x = hq - PW; }
+          else { const int r = hq - 2 * PW; y = 1 + (r >> 1); x = (r & 1) ? PW - 1 : 0; }
+          const int h = h0 - 1 + y, w = w0 - 1 + x;
+          const int hc = h < 0 ? 0 : h >= H ? H - 1 : h, wc = w < 0 ? 0 : w >= W ? W - 1 : w;
+          hin[u] = (hc == h && wc == w);
+          hpos[u] = (k0 + u < HALO_IT && hp < NHALO) ? y * PW + x : -1;
+          const long long off = ((long long)hc * W + wc) * STEM_C;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            dy[t] = bn_bwd(__ldg(dbase + t * fstride + off), __ldg(ybase + t * fstride + off));
+            hd[u][t] = __ldg(dbase + t * fstride + off);
+            hy[u][t] = __ldg(ybase + t * fstride + off);
           }
-        } else {
-#pragma unroll
-          for (int t = 0; t < T; ++t) dy[t] = 0.f;
         }
 #pragma unroll
-        for (int f = 1; f <= P; ++f) {
-          float o = 0.f;
+        for (int u = 0; u < HB; ++u) {
+          if (hpos[u] < 0) continue;
+          float dy[T];
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int tap = f - t + 2;
-            if (tap < 0 || tap > 4) continue;
-            o = fmaf(wtr[tap], dy[t], o);
+          for (int t = 0; t < T; ++t) dy[t] = hin[u] ? bn_bwd(hd[u][t], hy[u][t]) : 0.f;
+#pragma unroll
+          for (int f = 1; f <= P; ++f) {
+            float o = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const int tap = f - t + 2;
+              if (tap < 0 || tap > 4) continue;
+              o = fmaf(wtr[tap], dy[t], o);
+            }
+            dsp[((f - 1) * NPIX + hpos[u]) * STEM_DSLD + c] = o;
           }
-          dsp[((f - 1) * NPIX + y * PW + x) * STEM_DSLD + c] = o;
         }
       }
     }
