@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(NSLOT * STEM_C, 2)
 stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const float* __restrict__ ys,
                    const float* __restrict__ bnp, const float* __restrict__ coef, const float* __restrict__ wxy,
                    const float* __restrict__ wt, float* __restrict__ dwxy, float* __restrict__ dwt,
-                   float* __restrict__ dperc, int B, int H, int W, int relu_mask) {
+                   float* __restrict__ dperc, int B, int H, int W, int relu_mask, int l2pf) {
   constexpr int P = T - 2;
   constexpr int NT = NSLOT * STEM_C;
   constexpr int PW = BTW + 2, PH = BTH + 2, NPIX = PW * PH;
@@ -646,6 +646,27 @@ stem_bwd_pc_kernel(const StemFrames fr, const float* __restrict__ dpre, const fl
       }
     }
     __syncthreads();                                            // patch complete
+    if (l2pf && tile + (int)gridDim.x < ntiles) {
+      // L2 prefetch of the NEXT tile's d_pre / y rows (tile + halo): its halo ring and its first pixel pairs then pay an
+      // L2 round trip instead of a DRAM one
+      const int nt = tile + (int)gridDim.x;
+      const int nn = nt / (tiles_x * tiles_y);
+      const int nrem = nt - nn * tiles_x * tiles_y;
+      const int nh0 = (nrem / tiles_x) * BTH, nw0 = (nrem % tiles_x) * BTW;
+      constexpr int LPR = (PW * STEM_C * 4 + 127) / 128 + 1;    // 128-byte lines per tile row (unaligned start)
+      const int ws = nw0 > 0 ? nw0 - 1 : 0;
+      const long long row_end = (long long)W * STEM_C;          // floats per image row
+      for (int i = tid; i < 2 * T * PH * LPR; i += NT) {
+        const int line = i % LPR, r = i / LPR, y = r % PH, tt = (r / PH) % T, which = r / (PH * T);
+        const int h = nh0 - 1 + y;
+        const long long col = (long long)ws * STEM_C + line * 32;
+        if (h >= 0 && h < H && col < row_end) {
+          const float* pbase = which ? ys : dpre;
+          const float* q = pbase + (((long long)nn * T + tt) * H + h) * row_end + col;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+      }
+    }
     for (int pp = slot; pp < NPP; pp += NSLOT) {
       const int ly = pp / (BTW / 2), x0 = 2 * (pp - ly * (BTW / 2));
       const int h = h0 + ly, w = w0 + x0;
@@ -767,8 +788,10 @@ static int launch_stem_bwd_pc(const StemFrames& fr, const float* dpre, const flo
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
   const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
+  static int l2pf = -1;             // C3D_STEM_PF=1: L2 prefetch of the next tile's rows (default off: measured 4 % slower)
+  if (l2pf < 0) { const char* v = getenv("C3D_STEM_PF"); l2pf = v ? atoi(v) : 0; }
   stem_bwd_pc_kernel<T, BTW, BTH, NSLOT><<<grid, NSLOT * STEM_C, smem, st>>>(fr, dpre, ys, bnp, coef, wxy, wt, dwxy, dwt, dperc,
-                                                                              B, H, W, relu_mask);
+                                                                              B, H, W, relu_mask, l2pf);
   return c3d_check_last(cudaGetLastError());
 }
 
