@@ -29,6 +29,17 @@ def _reference(sd, pre, post, perc, wgt, dtype):
 @pytest.mark.parametrize("P,H,W,B", [(1, 20, 36, 2), (1, 19, 37, 3), (2, 24, 41, 2), (3, 17, 33, 2), (1, 64, 96, 2)])
 @pytest.mark.parametrize("impl,masked", [("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")])
 def test_stem_backward(P, H, W, B, impl, masked):
+    _run(P, H, W, B, impl, masked)
+
+
+@pytest.mark.parametrize("P,H,W,B", [(1, 256, 256, 4), (3, 128, 192, 4)])
+def test_stem_backward_persistent(P, H, W, B):
+    """More tiles than resident CTAs: every CTA of the (persistent) forward and backward kernels walks several tiles, so
+    the shared-memory hand-over between consecutive tiles of a CTA is on the path (1024 / 768 tiles on 296 / 592 CTAs)."""
+    _run(P, H, W, B, "1", "1")
+
+
+def _run(P, H, W, B, impl, masked):
     from change3d_b200 import engine
     from change3d_b200.model.x3d import create_x3d
     sd = O.synth_state_dict(O.x3d_schema(), 11)
