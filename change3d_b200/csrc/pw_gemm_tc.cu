@@ -50,6 +50,8 @@ struct Params {
   int ncat;          // 1: W hi / W lo column groups are interleaved per K chunk so that Ah x [Wh | Wl] is ONE MMA of 2 * NpB
                      // columns writing [main | correction] (correction at column NpB): A hi is read twice, not three times
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
+  int early;         // TMA path: the first copies of every producer warp are issued BEFORE the weights are staged (the
+                     // staging is ~5 K cycles per launch and used to sit in front of the first DRAM round trip)
   int pf_dist;       // TMA path: L2 prefetch distance in tiles (0 = off): the boxes of tile t + pf_dist are requested
                      // when tile t's copies are issued, so HBM latency is paid ahead of the shared-memory pipeline
   uint32_t rps;      // rows per batch sample, clamped to 2^31 - 1 (M < 2^31: all row arithmetic fits 32 bits)
@@ -261,6 +263,67 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+
+  const long long ntiles = (g.M + BM - 1) / BM;
+  const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * tpc;
+  const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
+  const int my_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const uint32_t stages_u32 = smem_u32(stages);
+  constexpr uint32_t STAGE_BYTES = 2 * STAGE_FLOATS * 4;     // hi + lo
+
+  // ---- producer cursors and the TMA issue step (used by the producer warps only) ----
+  // Chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage.  nstage is a multiple of nprod, so warp p
+  // handles chunks p, p + nprod, ... and cycles through its own stages p, p + nprod, ...; (tile, chunk, stage, phase)
+  // advance incrementally — no divisions in the loop.
+  // with WPS > 1 the warps of a group share the group's stages; warp `half` 0 issues the TMA copies
+  const int p = warp >= PROD_WARP0 ? (warp - PROD_WARP0) / WPS : 0, half = warp >= PROD_WARP0 ? (warp - PROD_WARP0) % WPS : 0;
+  const bool is_prod = warp >= PROD_WARP0 && p < P.nprod && my_tiles > 0;
+  const int own = P.nstage / P.nprod;
+  const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
+  struct Cursor { int ti, chunk, stage; uint32_t phase; };
+  auto advance = [&](Cursor& c) {
+    c.chunk += P.nprod;
+    while (c.chunk >= nchunks) { c.chunk -= nchunks; ++c.ti; }
+    c.stage += P.nprod;
+    if (c.stage >= P.nstage) { c.stage -= P.nstage; c.phase ^= 1u; }
+  };
+  auto issue = [&](const Cursor& c) {      // wait for the stage to drain, then start the TMA copy of the raw rows
+    DBG_T(d_a, mbar_wait(smem_u32(empty + c.stage), c.phase ^ 1u, (uint32_t)P.wait_hint));
+    if (lane == 0) {
+      const int r0 = (int)((t_begin + c.ti) * BM);
+      const uint32_t dst = stages_u32 + (uint32_t)c.stage * STAGE_BYTES;
+      const uint32_t bar = smem_u32(rawfull + c.stage);
+      mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
+      tma_load_2d(dst, &tmA, c.chunk * KC, r0, bar);
+      if (has2) tma_load_2d(dst + STAGE_FLOATS * 4, &tmA2, c.chunk * KC, r0, bar);
+      if (P.pf_dist) {
+        // the first tile also requests the tiles in between (nothing was requested for them yet)
+        for (int pt = c.ti == 0 ? 1 : c.ti + P.pf_dist; pt <= c.ti + P.pf_dist && pt < my_tiles; ++pt) {
+          const int pr = (int)((t_begin + pt) * BM);
+          tma_prefetch_2d(&tmA, c.chunk * KC, pr);
+          if (has2) tma_prefetch_2d(&tmA2, c.chunk * KC, pr);
+        }
+      }
+    }
+    __syncwarp();
+  };
+  Cursor cur, nxt;
+  cur.ti = 0; cur.chunk = p; cur.stage = p; cur.phase = 0;
+  while (cur.chunk >= nchunks) { cur.chunk -= nchunks; ++cur.ti; }
+  nxt = cur;
+  auto pre_issue = [&]() {                 // the first own - 1 stages of this producer warp
+    for (int i = 0; i < own - 1; ++i) { if (nxt.ti < my_tiles && half == 0) issue(nxt); advance(nxt); }
+  };
+  const bool early = P.tma && P.early;
+  if (early) {
+    __syncthreads();                       // the mbarrier inits are visible to the lanes that arm them
+    if (is_prod) {
+      pdl_wait();                          // the operand rows are an earlier kernel's output
+      pre_issue();                         // in flight while all warps stage the weights below
+    }
+  }
+
   // Programmatic dependent launch: everything up to here touches no global memory.  Model parameters are constant
   // within a step, so their staging below may also overlap the previous kernel's tail; other weights wait first.
   if (!g.w_const) pdl_wait();
@@ -328,58 +391,11 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
   pdl_trigger();     // tensor memory is allocated: the next kernel's CTAs may start their own setup
   pdl_wait();        // operands, BN blocks, statistics: produced by earlier kernels
 
-  const long long ntiles = (g.M + BM - 1) / BM;
-  const long long tpc = (ntiles + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = (long long)blockIdx.x * tpc;
-  const long long t_end = t_begin + tpc < ntiles ? t_begin + tpc : ntiles;
-  const int my_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
-  const uint32_t stages_u32 = smem_u32(stages);
-  constexpr uint32_t STAGE_BYTES = 2 * STAGE_FLOATS * 4;     // hi + lo
-
   if (warp >= PROD_WARP0) {
     // ===================== producers =====================
-    // Chunk c of this CTA (tile-major, then K chunk) uses stage c % nstage.  nstage is a multiple of nprod, so warp p
-    // handles chunks p, p + nprod, ... and cycles through its own stages p, p + nprod, ...; (tile, chunk, stage, phase)
-    // advance incrementally — no divisions in the loop.
-    // with WPS > 1 the warps of a group share the group's stages; warp `half` 0 issues the TMA copies
-    const int p = (warp - PROD_WARP0) / WPS, half = (warp - PROD_WARP0) % WPS;
     const int bg0 = half * (16 / WPS), bg1 = bg0 + 16 / WPS;          // this warp's 8-row groups of a chunk
-    if (p < P.nprod && my_tiles > 0) {
-      const int own = P.nstage / P.nprod;
-      const bool has2 = (a.mode == PRO_BNBWD || a.mode == PRO_ABSDIFF || a.mode == PRO_MASK_POS);
-      struct Cursor { int ti, chunk, stage; uint32_t phase; };
-      auto advance = [&](Cursor& c) {
-        c.chunk += P.nprod;
-        while (c.chunk >= nchunks) { c.chunk -= nchunks; ++c.ti; }
-        c.stage += P.nprod;
-        if (c.stage >= P.nstage) { c.stage -= P.nstage; c.phase ^= 1u; }
-      };
-      auto issue = [&](const Cursor& c) {      // wait for the stage to drain, then start the TMA copy of the raw rows
-        DBG_T(d_a, mbar_wait(smem_u32(empty + c.stage), c.phase ^ 1u, (uint32_t)P.wait_hint));
-        if (lane == 0) {
-          const int r0 = (int)((t_begin + c.ti) * BM);
-          const uint32_t dst = stages_u32 + (uint32_t)c.stage * STAGE_BYTES;
-          const uint32_t bar = smem_u32(rawfull + c.stage);
-          mbar_expect_tx(bar, (uint32_t)(STAGE_FLOATS * 4 * (has2 ? 2 : 1)));
-          tma_load_2d(dst, &tmA, c.chunk * KC, r0, bar);
-          if (has2) tma_load_2d(dst + STAGE_FLOATS * 4, &tmA2, c.chunk * KC, r0, bar);
-          if (P.pf_dist) {
-            // the first tile also requests the tiles in between (nothing was requested for them yet)
-            for (int pt = c.ti == 0 ? 1 : c.ti + P.pf_dist; pt <= c.ti + P.pf_dist && pt < my_tiles; ++pt) {
-              const int pr = (int)((t_begin + pt) * BM);
-              tma_prefetch_2d(&tmA, c.chunk * KC, pr);
-              if (has2) tma_prefetch_2d(&tmA2, c.chunk * KC, pr);
-            }
-          }
-        }
-        __syncwarp();
-      };
-      Cursor cur, nxt;
-      cur.ti = 0; cur.chunk = p; cur.stage = p; cur.phase = 0;
-      while (cur.chunk >= nchunks) { cur.chunk -= nchunks; ++cur.ti; }
-      nxt = cur;
-      if (P.tma)
-        for (int i = 0; i < own - 1; ++i) { if (nxt.ti < my_tiles && half == 0) issue(nxt); advance(nxt); }
+    if (is_prod) {
+      if (P.tma && !early) pre_issue();
       while (cur.ti < my_tiles) {
         float* a_hi = stages + (size_t)cur.stage * 2 * STAGE_FLOATS;
         float* a_lo = a_hi + STAGE_FLOATS;
@@ -984,6 +1000,10 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
     bool ok = tc::make_tmap_rows(&tmA, g.a.A, g.a.K, g.M, g.a.ld, tc::BM);
     if (ok && has2) ok = tc::make_tmap_rows(&tmA2, g.a.A2, g.a.K, g.M, g.a.ld, tc::BM);
     P.tma = ok ? 1 : 0;
+  }
+  {
+    static const int early_env = getenv("C3D_TC_EARLY") ? atoi(getenv("C3D_TC_EARLY")) : 0;   // measured neutral: off
+    P.early = early_env ? 1 : 0;
   }
   P.pf_dist = 0;
   if (P.tma) {
