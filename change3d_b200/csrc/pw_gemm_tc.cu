@@ -52,6 +52,7 @@ struct Params {
   int epi_bufs;      // staging tiles per epilogue warp: 2 when the Swish-backward statistics need the second one
   int early;         // TMA path: the first copies of every producer warp are issued BEFORE the weights are staged (the
                      // staging is ~5 K cycles per launch and used to sit in front of the first DRAM round trip)
+  int epar;          // 1: the Swish-backward epilogue reads its per-column parameters from shared memory (staged at setup)
   int pf_dist;       // TMA path: L2 prefetch distance in tiles (0 = off): the boxes of tile t + pf_dist are requested
                      // when tile t's copies are issued, so HBM latency is paid ahead of the shared-memory pipeline
   uint32_t rps;      // rows per batch sample, clamped to 2^31 - 1 (M < 2^31: all row arithmetic fits 32 bits)
@@ -246,7 +247,9 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
   float* stages = B_hi + (size_t)2 * NpB * K;                       // nstage x (A_hi, A_lo)
   float* epi = stages + (size_t)P.nstage * 2 * STAGE_FLOATS;        // NEPI warps x epi_bufs x [32][EPI_LD]
   float* s_stat = epi + NEPI * P.epi_bufs * 32 * EPI_LD;            // [NEPI warps][2][NpA]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + NEPI * 2 * P.NpA);
+  float* s_epar = s_stat + NEPI * 2 * P.NpA;                       // [6][NpA] Swish-backward epilogue: mean, rstd, scale, beta of
+                                                                    // this CTA's columns + the SE gates of its first two samples
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epar + 6 * P.NpA);
   uint64_t* full = bars;                  // [nstage]
   uint64_t* empty = bars + P.nstage;      // [nstage]
   uint64_t* rawfull = empty + P.nstage;   // [nstage] TMA bytes of the raw rows have landed
@@ -380,6 +383,27 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
       }
     }
     for (int i = threadIdx.x; i < NEPI * 2 * P.NpA; i += NTHREADS) s_stat[i] = 0.f;
+  }
+  // C3D_TC_EPAR=1: Swish-backward epilogue parameters of this CTA's columns staged once in shared memory instead of being
+  // fetched (L1 / L2) in every (tile, column chunk) step; the SE gates of the CTA's first two batch samples ride along
+  // (a CTA's tiles are consecutive rows), later samples fall back to global loads.  Measured neutral (21.62 / 21.65 vs
+  // 21.62 / 21.59 ms over the family) although removing the loads altogether is worth 0.16 ms: kept as a switch, off.
+  const uint32_t esamp0 = (uint32_t)(t_begin * BM) / P.rps;
+  if (g.epi == EPI_SWISH_BWD && P.epar) {
+    pdl_wait();                              // BN blocks / gates are an earlier kernel's output
+    for (int i = threadIdx.x; i < 6 * P.NpA; i += NTHREADS) {
+      const int r = i / P.NpA, cidx = i - r * P.NpA, col = n0 + cidx;
+      float v = r == 1 || r == 2 || r >= 4 ? 1.f : 0.f;
+      if (cidx < NpB && col < g.Ns) {
+        if (r == 0) v = __ldg(BNP_MEAN(g.ebnp, g.Ns) + col);
+        else if (r == 1) v = __ldg(BNP_RSTD(g.ebnp, g.Ns) + col);
+        else if (r == 2) v = __ldg(BNP_SCALE(g.ebnp, g.Ns) + col);
+        else if (r == 3) v = __ldg(BNP_BETA(g.ebnp, g.Ns) + col);
+        else if (g.egate && (long long)(esamp0 + (uint32_t)(r - 4)) * P.rps < g.M)
+          v = __ldg(g.egate + (long long)(esamp0 + (uint32_t)(r - 4)) * g.Ns + col);
+      }
+      s_epar[i] = v;
+    }
   }
   const long long d_tw1 = dbg_on ? clock64() : 0;
   fence_proxy_async();
@@ -633,12 +657,25 @@ __global__ void __launch_bounds__((NEPI + 1 + NPROD) * 32, CPS) pw_gemm_tc_kerne
         } else {
           float4 mean = f4zero(), rstd = f4zero(), scale = f4zero(), beta = f4zero();
           float4 gt0 = make_float4(1.f, 1.f, 1.f, 1.f), gt1 = gt0;
-          if (g.epi == EPI_SWISH_BWD && col_ok) {
+          if (g.epi == EPI_SWISH_BWD && col_ok && !P.epar) {
             mean = ldg4(BNP_MEAN(g.ebnp, g.Ns) + col); rstd = ldg4(BNP_RSTD(g.ebnp, g.Ns) + col);
             scale = ldg4(BNP_SCALE(g.ebnp, g.Ns) + col); beta = ldg4(BNP_BETA(g.ebnp, g.Ns) + col);
             if (g.egate && sp_fast) {
               gt0 = ldg4(g.egate + wsp0 * g.Ns + col);
               if (wsplit < 32 && wrow0 + wsplit < g.M) gt1 = ldg4(g.egate + (wsp0 + 1) * g.Ns + col);
+            }
+          } else if (g.epi == EPI_SWISH_BWD && col_ok) {
+            const float* ep = s_epar + cl;                    // staged at setup: [mean | rstd | scale | beta | gate s0 | gate s0 + 1]
+            mean = *reinterpret_cast<const float4*>(ep); rstd = *reinterpret_cast<const float4*>(ep + P.NpA);
+            scale = *reinterpret_cast<const float4*>(ep + 2 * P.NpA); beta = *reinterpret_cast<const float4*>(ep + 3 * P.NpA);
+            if (g.egate && sp_fast) {
+              const long long rel = wsp0 - (long long)esamp0;
+              if (rel >= 0 && rel <= 1) gt0 = *reinterpret_cast<const float4*>(ep + (4 + rel) * P.NpA);
+              else gt0 = ldg4(g.egate + wsp0 * g.Ns + col);
+              if (wsplit < 32 && wrow0 + wsplit < g.M) {
+                if (rel == 0) gt1 = *reinterpret_cast<const float4*>(ep + 5 * P.NpA);
+                else gt1 = ldg4(g.egate + (wsp0 + 1) * g.Ns + col);
+              }
             }
           }
           // This step's E1 values were requested one step ago (e1n).  The next step's are requested quad by quad right
@@ -906,7 +943,7 @@ static bool tc_plan(tc::Params& P, size_t budget, int max_npa, int min_stage, in
     NpB = ((Np / 16 + nsplit - 1) / nsplit) * 16;
     const int NpA = (NpB + 31) / 32 * 32;
     if (NpA > max_npa) continue;
-    fixed = (size_t)2 * NpB * K * 4 + (size_t)NEPI * P.epi_bufs * 32 * tc::EPI_LD * 4 + (size_t)NEPI * 2 * NpA * 4 + 512;
+    fixed = (size_t)2 * NpB * K * 4 + (size_t)NEPI * P.epi_bufs * 32 * tc::EPI_LD * 4 + (size_t)NEPI * 2 * NpA * 4 + (size_t)6 * NpA * 4 + 512;
     if (fixed + (size_t)min_stage * 2 * tc::STAGE_FLOATS * 4 <= budget) break;
     if (NpB <= 16) return false;
   }
@@ -1005,6 +1042,7 @@ int c3d_launch_pw_gemm_tc(const GemmArgs& g0, int num_sms, cudaStream_t stream, 
     static const int early_env = getenv("C3D_TC_EARLY") ? atoi(getenv("C3D_TC_EARLY")) : 0;   // measured neutral: off
     P.early = early_env ? 1 : 0;
   }
+  { static const int epar_env = getenv("C3D_TC_EPAR") ? atoi(getenv("C3D_TC_EPAR")) : 0;   /* measured neutral: off */ P.epar = epar_env ? 1 : 0; }
   P.pf_dist = 0;
   if (P.tma) {
     static const int pf_env = getenv("C3D_L2PF") ? atoi(getenv("C3D_L2PF")) : 0;       // 0 off (default: measured 1-4 % slower, profiles/r02_summary.md), -1 auto, n tiles
