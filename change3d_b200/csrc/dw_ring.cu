@@ -119,8 +119,8 @@ __device__ __forceinline__ Unit decode(long long step, long long s1, const Geo& 
 // forward
 // ------------------------------------------------------------------------------------------------
 // PAIR: thread = (pair of adjacent channels, group of 2 columns) with packed FFMA2 arithmetic; else (channel, 4 columns)
-template <int T, bool PAIR>
-__global__ void __launch_bounds__(NT, 2) dw_fwd_ring_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
+template <int T, bool PAIR, bool ONE>
+__global__ void __launch_bounds__(NT, ONE ? 1 : 2) dw_fwd_ring_kernel(const float* __restrict__ X, const float* __restrict__ bnp,
                                                             const float* __restrict__ w, float* __restrict__ Y,
                                                             double* __restrict__ stats, const Geo G) {
   pdl_trigger();   // programmatic dependent launch: let the next kernel start its setup,
@@ -367,8 +367,10 @@ struct FuseArgs {
   const float* coef_b;   // [2][Cs]
 };
 
-template <int T, bool FUSED>
-__global__ void __launch_bounds__(NT, 2) dw_bwd_ring_kernel(const float* __restrict__ DY, const float* __restrict__ YA,
+// ONE: one CTA per SM with the whole register file (no 128-register cap).  T >= 4 always runs that way (its ring does not fit
+// twice); measured on the T = 5 / T = 4 configurations: 11.4 -> 7.5 ms and 15.2 -> 11.6 ms per step against the capped build.
+template <int T, bool FUSED, bool ONE>
+__global__ void __launch_bounds__(NT, ONE ? 1 : 2) dw_bwd_ring_kernel(const float* __restrict__ DY, const float* __restrict__ YA,
                                                             const float* __restrict__ bnp_a, const float* __restrict__ w,
                                                             float* __restrict__ DR, float* __restrict__ dW,
                                                             double* __restrict__ stats_a, const Geo G, const FuseArgs F) {
@@ -991,64 +993,50 @@ int c3d_launch_dw_fwd_ring(const float* X, const float* bnp, const float* w, flo
   size_t smem = 0;
   int grid = 0;
   const size_t extra = (size_t)(4 * dwr::CB * 4 + 2 * dwr::CB * 8);        // s_bn [4][CB] floats + s_st [2][CB] doubles
-  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1)) return -1;
+  // two CTAs per SM when the ring fits twice (T = 3 always; T = 4 with depth 2, T = 5 with depth 1), else one.
+  // C3D_DW_OCC=1 restores the round-1 choice (one CTA per SM for T >= 4).
+  // C3D_DW_FWD_OCC=1: one CTA per SM with the whole register file for every T (timing experiment switch)
+  const bool occ1 = (dwr::env_int("C3D_DW_OCC", 2) < 2 && T != 3) || dwr::env_int("C3D_DW_FWD_OCC", 2) < 2;
+  bool one = occ1;
+  if (occ1 || !dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, 2)) {
+    if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, 1)) return -1;
+    one = true;
+  }
   // channel-pair FFMA2 arithmetic (C3D_DW_PAIR=0: one channel x four columns per thread, scalar FFMA); pairs need an even
   // channel stride and 8-byte aligned tensors
   const bool pair = dwr::env_int("C3D_DW_PAIR", 1) && (Cs & 1) == 0 && ((reinterpret_cast<uintptr_t>(Y) & 7) == 0);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+#define FWD_GO(T_, P_, O_) do {                                                                                          \
+    e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<T_, P_, O_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return C3D_ERR_SMEM;                                                                          \
+    c3d_launch_pdl(dwr::dw_fwd_ring_kernel<T_, P_, O_>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G); } while (0)
+#define FWD_T(T_) do { if (pair) { if (one) FWD_GO(T_, true, true); else FWD_GO(T_, true, false); }                      \
+                       else { if (one) FWD_GO(T_, false, true); else FWD_GO(T_, false, false); } } while (0)
   switch (T) {
-    case 3:
-      if (pair) {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      } else {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<3, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      }
-      break;
-    case 4:
-      if (pair) {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      } else {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<4, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      }
-      break;
-    default:
-      if (pair) {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5, true>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      } else {
-        e = cudaFuncSetAttribute(dwr::dw_fwd_ring_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return C3D_ERR_SMEM;
-        c3d_launch_pdl(dwr::dw_fwd_ring_kernel<5, false>, dim3(grid), dim3(dwr::NT), smem, st, X, bnp, w, Y, stats, G);
-      }
-      break;
+    case 3: FWD_T(3); break;
+    case 4: FWD_T(4); break;
+    default: FWD_T(5); break;
   }
+#undef FWD_T
+#undef FWD_GO
   return c3d_check_last(cudaGetLastError());
 }
 
 // fuse == nullptr: dy = du already transformed by the elementwise pre-pass (dw_dy_kernel); else the raw du plus the
 // BN_b / SE backward operands (transform fused into the ring fill).  Returns -1 when not handled here.
-template <int T>
+template <int T, bool ONE>
 static int launch_bwd(const float* dy, const float* ya, const float* bnp_a, const float* w, float* dr, float* dW, double* stats_a,
                       const dwr::Geo& G, const dwr::FuseArgs* fuse, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
   if (fuse) {
-    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, true, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return C3D_ERR_SMEM;
-    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, true>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, *fuse);
+    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, true, ONE>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, *fuse);
   } else {
     dwr::FuseArgs none = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(dwr::dw_bwd_ring_kernel<T, false, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return C3D_ERR_SMEM;
-    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, false>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, none);
+    c3d_launch_pdl(dwr::dw_bwd_ring_kernel<T, false, ONE>, dim3(grid), dim3(dwr::NT), smem, st, dy, ya, bnp_a, w, dr, dW, stats_a, G, none);
   }
   return c3d_check_last(cudaGetLastError());
 }
@@ -1063,13 +1051,17 @@ int c3d_launch_dw_bwd_ring(const float* dy, const float* ya, const float* bnp_a,
   const bool fused = yb != nullptr;
   // s_dw [27][CB] floats (+ pad) + s_st [2][CB] doubles + s_cb [7][CB] floats
   const size_t extra = (size_t)(28 * dwr::CB * 4 + 2 * dwr::CB * 8 + 8 * dwr::CB * 4);
-  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, T == 3 ? 2 : 1, fused)) return -1;
+  // C3D_DW_BWD_OCC: CTAs per SM of the T = 3 kernel (2: 128-register build, 1: whole register file, one CTA per SM)
+  const bool one3 = dwr::env_int("C3D_DW_BWD_OCC", 1) < 2;      // measured: 9.67 -> 9.34 ms per step (profiles/r02_summary.md section 2.7)
+  if (!dwr::plan(G, T, N, IH, IW, C, Cs, extra, smem, grid, (T == 3 && !one3) ? 2 : 1, fused)) return -1;
   dwr::FuseArgs F = {yb, bnp_b, gate, dpool, coef_b};
   const dwr::FuseArgs* fp = fused ? &F : nullptr;
   switch (T) {
-    case 3: return launch_bwd<3>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
-    case 4: return launch_bwd<4>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
-    default: return launch_bwd<5>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+    case 3:
+      if (one3) return launch_bwd<3, true>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+      return launch_bwd<3, false>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+    case 4: return launch_bwd<4, true>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
+    default: return launch_bwd<5, true>(dy, ya, bnp_a, w, dr, dW, stats_a, G, fp, grid, smem, st);
   }
 }
 
